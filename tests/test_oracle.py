@@ -1,0 +1,154 @@
+"""CPU tests: the oracle against the reference's own known answers and cached solutions."""
+import numpy as np
+import pytest
+
+from oracle import configs as C
+from oracle import cport as CP
+from oracle import isomorphisms as iso
+from oracle import knot as KN
+from oracle import systems as S
+from tests import golden_util as GU
+
+
+# ---- isomorphism KATs (reference: src/quantum/primitives/isomorphisms.jl:471-643) ---------
+def test_ket_iso_kat():
+    psi = np.array([-1j, 2 + 3j])
+    assert np.array_equal(iso.ket_to_iso(psi), [0, 2, -1, 3])            # :473
+    assert np.allclose(iso.iso_to_ket(iso.ket_to_iso(psi)), psi)
+
+
+def test_operator_iso_vec_kat():
+    assert np.array_equal(iso.operator_to_iso_vec(np.eye(2)), [1, 0, 0, 0, 0, 1, 0, 0])   # :479
+    XY = np.array([[0, 1 - 1j], [1 + 1j, 0]])
+    assert np.array_equal(iso.operator_to_iso_vec(XY), [0, 1, 0, 1, 1, 0, -1, 0])          # :497-508
+    assert np.allclose(iso.iso_vec_to_operator(iso.operator_to_iso_vec(XY)), XY)
+
+
+def test_hamiltonian_iso_kat():
+    Hc = np.array([[1, 2], [3, 4]]) + 1j * np.array([[0, 1], [1, 0]])
+    GH = iso.G(Hc)
+    assert np.allclose(GH, [[0, 1, 1, 2], [1, 0, 3, 4], [-1, -2, 0, 1], [-3, -4, 1, 0]])  # :630
+    assert np.allclose(iso.iso(Hc), [[1, 2, 0, -1], [3, 4, -1, 0], [0, 1, 1, 2], [1, 0, 3, 4]])
+    assert np.allclose(iso.H_of_G(GH), Hc)
+    assert np.allclose(iso.ad_vec(S.PAULI_X.real),
+                       [[0, 1, -1, 0], [1, 0, 0, -1], [-1, 0, 0, 1], [0, -1, 1, 0]])      # :636
+    assert np.allclose(iso.ad_vec(S.PAULI_Y),
+                       np.array([[0, -1j, -1j, 0], [1j, 0, 0, -1j], [1j, 0, 0, -1j], [0, 1j, 1j, 0]]))
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 6])
+def test_compact_density_iso(n):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    rho = A + A.conj().T
+    x = iso.density_to_compact_iso(rho)
+    L, P = iso.density_lift_matrix(n), iso.density_projection_matrix(n)
+    assert x.size == n * n
+    assert np.count_nonzero(L) == n * (2 * n - 1)                       # :571
+    assert np.allclose(P @ L, np.eye(n * n))                           # P L = I
+    assert np.allclose(L @ x, iso.density_to_iso_vec(rho))
+    assert np.allclose(P @ iso.density_to_iso_vec(rho), x)
+    assert np.allclose(iso.compact_iso_to_density(x), rho)
+
+
+def test_compact_density_order_2x2():
+    a, b, c, d = 0.7, 0.3, 0.1, -0.2
+    rho = np.array([[a, c + 1j * d], [c - 1j * d, b]])
+    assert np.allclose(iso.density_to_compact_iso(rho), [a, c, b, d])   # :610-617
+
+
+def test_lindbladian_is_trace_preserving_and_matches_master_equation():
+    rng = np.random.default_rng(7)
+    n = 3
+    Hh = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    Hh = Hh + Hh.conj().T
+    Lop = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    rho = A @ A.conj().T
+    sys_ = S.OpenQuantumSystem(Hh, [], [], [Lop])
+    G0, _ = S.compact_generator_parts(sys_)
+    drho = -1j * (Hh @ rho - rho @ Hh) + Lop @ rho @ Lop.conj().T \
+        - 0.5 * (Lop.conj().T @ Lop @ rho + rho @ Lop.conj().T @ Lop)
+    assert np.allclose(G0 @ iso.density_to_compact_iso(rho), iso.density_to_compact_iso(drho))
+
+
+# ---- golden trajectories: the reference's converged solutions satisfy OUR residual ---------
+@pytest.mark.parametrize("name", sorted(GU.TIGHT))
+def test_golden_residual_is_zero(name):
+    p, Z = GU.load(name)
+    assert np.abs(KN.residual(p, Z)).max() < GU.TIGHT[name]
+    assert np.abs(CP.residual(p, Z)).max() < GU.TIGHT[name]
+
+
+def test_golden_layout_two_qubit():
+    p, Z = GU.load("two_qubit_zoh")
+    dt, t = Z[p.dt_off], Z[p.dt_off + 1]
+    assert np.ptp(dt) < 1e-12                                    # timesteps_all_equal
+    assert np.allclose(np.cumsum(dt[:-1]), t[1:], atol=1e-9)
+    assert np.all(Z[p.u_off:p.u_off + p.m, 0] == 0)              # initial control pin
+    u, du, ddu = (Z[p.u_off + i * p.m:p.u_off + (i + 1) * p.m] for i in range(3))
+    assert np.abs(u[:, 1:] - u[:, :-1] - dt[:-1] * du[:, :-1]).max() < 1e-12   # DerivativeIntegrator
+    U = iso.iso_vec_to_operator(Z[:32, -1])
+    assert abs(np.trace(S.GATE_CX.conj().T @ U)) ** 2 / 16 > 0.999999          # solved CX gate
+
+
+# ---- the two oracle implementations agree; derivatives agree with finite differences -------
+@pytest.mark.parametrize("cfg,K", [(1, 12), (2, 8), (3, 5), (4, 8), (6, 8)])
+def test_python_oracle_vs_c_port(cfg, K):
+    p, Z, mu = C.trajectory(cfg, K)
+    assert np.abs(KN.residual(p, Z) - CP.residual(p, Z)).max() < 1e-13
+    assert np.abs(KN.jacobian_values(p, Z) - CP.jacobian_values(p, Z)).max() < 1e-12
+    assert np.abs(KN.hessian_values(p, Z, mu) - CP.hessian_values(p, Z, mu)).max() < 1e-10
+
+
+@pytest.mark.parametrize("name", ["systems_cat_density", "trajectories_density"])
+def test_c_port_on_large_norm_golden(name):
+    p, Z = GU.load(name)       # ||dt G||_1 up to 14.8: exercises scaling in the Taylor action
+    mu = np.random.default_rng(0).standard_normal(p.dim)
+    assert np.abs(KN.jacobian_values(p, Z) - CP.jacobian_values(p, Z)).max() < 1e-11
+    h1, h2 = KN.hessian_values(p, Z, mu), CP.hessian_values(p, Z, mu)
+    assert np.abs(h1 - h2).max() < 1e-9 * max(1.0, np.abs(h1).max())
+
+
+@pytest.mark.parametrize("cfg,K", [(1, 5), (2, 4), (4, 4), (6, 4)])
+def test_jacobian_and_hessian_vs_finite_differences(cfg, K):
+    p, Z, mu = C.trajectory(cfg, K)
+    n = p.D * p.K
+    rows, cols = KN.jacobian_structure(p)
+    J = KN.dense(KN.jacobian_values(p, Z), rows, cols, (p.dim, n))
+    assert J.shape == (p.dim, p.D * p.K + p.global_dim)          # integrators.jl:780-782
+    z0 = Z.reshape(-1, order="F")
+    h = 1e-6
+    Jfd = np.zeros_like(J)
+    for c in range(n):
+        zp, zm = z0.copy(), z0.copy()
+        zp[c] += h
+        zm[c] -= h
+        Jfd[:, c] = (KN.residual(p, zp.reshape(p.D, p.K, order="F"))
+                     - KN.residual(p, zm.reshape(p.D, p.K, order="F"))) / (2 * h)
+    assert np.abs(J - Jfd).max() < 1e-7
+    hr, hc = KN.hessian_structure(p)
+    assert np.all(hr <= hc)
+    Hu = KN.dense(KN.hessian_values(p, Z, mu), hr, hc, (n, n))
+    Hs = Hu + np.triu(Hu, 1).T
+    # d/dz (J^T mu) by central differences of the analytic Jacobian
+    Hfd = np.zeros((n, n))
+    for c in range(n):
+        zp, zm = z0.copy(), z0.copy()
+        zp[c] += h
+        zm[c] -= h
+        gp = KN.dense(KN.jacobian_values(p, zp.reshape(p.D, p.K, order="F")), rows, cols, (p.dim, n)).T @ mu
+        gm = KN.dense(KN.jacobian_values(p, zm.reshape(p.D, p.K, order="F")), rows, cols, (p.dim, n)).T @ mu
+        Hfd[:, c] = (gp - gm) / (2 * h)
+    assert np.abs(Hs - Hfd).max() < 1e-5 * max(1.0, np.abs(Hs).max())
+
+
+def test_structure_counts():
+    for cfg, nj, nh in [(1, 48 + 8, None), (2, 416 + 32, 175), (3, 2688 + 128, 655), (4, 304 + 16, 54)]:
+        p, _, _ = C.problem(cfg, 3)[0], None, None
+        assert p.nnz_jac_knot == nj
+        if nh is not None:
+            assert p.nnz_hess_knot == nh
+        r, c = KN.jacobian_structure(p)
+        assert r.dtype == np.int64 and r.min() == 1 and r.max() == p.dim
+        assert len(set(zip(r.tolist(), c.tolist()))) == r.size    # no duplicates emitted
