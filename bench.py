@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Benchmark of the knot path: knot-constraint + Jacobian evals / second.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 3]
+
+A "step" is one Ipopt-callback's worth of work: the fused residual + Jacobian evaluation of
+every knot of one trajectory (BASELINE.json config C3: 3-transmon unitary, d=8 (iso dim 128),
+4 drives, K=1000 knots -> 999 knot evals per step per GPU).  N > 1: weak scaling, every rank owns
+999 knot evals of a (999 N + 1)-knot trajectory and each step ends with ONE all-gather of the
+[delta | Jacobian values] shards (NCCL).  Prints one JSON line on rank 0.
+
+`--impl reference`: the reference is 100% Julia and no Julia toolchain exists here, so this arm
+times the C++ port of the reference's algorithm (oracle/c/knot_ref.cpp) on all host threads.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "knot_constraint_jacobian_evals_per_sec"
+UNIT = "evals/s"
+L2_BYTES = 126 * 2 ** 20
+
+
+def algorithmic_bytes_per_eval(p):
+    """8 * [(n_x + m + 1) read + (n_x + n_b b^2 + n_x m + n_x) written]
+    (the constant identity block is excluded)."""
+    return 8 * ((p.n_x + p.m + 1) + (p.n_x + p.n_b * p.b * p.b + p.n_x * p.m + p.n_x))
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(workload)
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period, self.stop_flag = index, period, False
+        self.sm, self.reasons, self.max_mhz, self.err = [], 0, None, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while True:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    self.reasons |= nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    self.reasons |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                if self.stop_flag:
+                    break
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing: report, never fake
+            self.err = repr(e)
+
+    def summary(self):
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+                 0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+                 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+                 0x100: "display_clock_setting"}
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+               "sm_max_mhz": self.max_mhz, "samples": len(self.sm),
+               "reasons": [n for b, n in names.items() if self.reasons & b and n != "gpu_idle"]}
+        if self.err:
+            out["error"] = self.err
+        return out
+
+
+def run_reference(args):
+    """CPU arm: the C++ port of the reference algorithm, all host threads, bounded steps."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import configs as C
+    from oracle import cport as CP
+    p, Z, _ = C.trajectory(args.config)
+    threads = CP.max_threads()
+    evals = p.K - 1
+
+    def step():
+        CP.residual(p, Z, threads)
+        CP.jacobian_values(p, Z, threads)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = evals * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(p, args.config, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} passes over the {evals}-eval C{args.config} trajectory "
+                                   "(residual + Jacobian), C++ port of the reference's expv+dual algorithm; "
+                                   "the Julia reference itself cannot run here (no Julia toolchain)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(p, cfg, n_gpus):
+    return {"workload": f"C{cfg}: {p.kind} d={p.b // 2 if p.kind != 'density' else int(round(p.b ** 0.5))} "
+                        f"(iso n_x={p.n_x}) m={p.m} drives, K={p.K} knots per GPU "
+                        f"({p.K - 1} knot evals/step/GPU), fused residual+Jacobian",
+            "knots_per_gpu": p.K, "n_x": p.n_x, "drives": p.m, "D": p.D,
+            "parallelism": f"knot-sharded x{n_gpus}" if n_gpus > 1 else "single GPU"}
+
+
+def cpu_baseline(p, Z, budget_s=12.0):
+    from oracle import cport as CP
+    threads = CP.max_threads()
+    CP.residual(p, Z, threads)
+    CP.jacobian_values(p, Z, threads)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        CP.residual(p, Z, threads)
+        CP.jacobian_values(p, Z, threads)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 2000:
+            break
+    return {"value": (p.K - 1) * n / el, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} passes over the {p.K - 1}-eval trajectory in {el:.1f} s "
+                      "(oracle/c/knot_ref.cpp: Taylor expv + forward jets, std::thread over knots)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import piccolo_b200 as pb
+    from oracle import configs as C   # input generator + cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this benchmark has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    p, Z, _ = C.trajectory(args.config)
+    n_eval = p.K - 1
+    B = pb.B200BilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off,
+                                  dt_off=p.dt_off, u_off=p.u_off, device=local,
+                                  knot0=rank * n_eval, algorithm=args.algorithm)
+    chunk = B.dim + B.nnz_jac            # doubles this rank contributes per step
+    # rotating buffer sets so that consecutive steps never find their lines in L2
+    set_bytes = 8 * (chunk * world + p.D * p.K)
+    nsets = max(2, int(np.ceil(2.2 * L2_BYTES / set_bytes)))
+    rng = np.random.default_rng(rank)
+    zflat = Z.reshape(-1, order="F")
+    Zs, outs = [], []
+    for s in range(nsets):
+        zz = zflat.copy()
+        if s:  # distinct data per set (tiny perturbation of the controls' low bits is enough)
+            zz += 1e-9 * rng.standard_normal(zz.size)
+        Zs.append(torch.from_numpy(zz).to(dev))
+        outs.append(torch.empty(chunk * world, dtype=torch.float64, device=dev))
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        s = i % nsets
+        slot = outs[s][rank * chunk:(rank + 1) * chunk]
+        B.residual_jacobian_device(Zs[s], slot[:B.dim], slot[B.dim:], stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(outs[s], slot)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = B.launch_count
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for i in range(args.steps):
+        s = i % nsets
+        slot = outs[s][rank * chunk:(rank + 1) * chunk]
+        kev[i][0].record()
+        B.residual_jacobian_device(Zs[s], slot[:B.dim], slot[B.dim:], stream.cuda_stream)
+        kev[i][1].record()
+        if world > 1:
+            dist.all_gather_into_tensor(outs[s], slot)
+    t_end.record()
+    barrier()
+    launches = B.launch_count - l0
+    total_ms = t_start.elapsed_time(t_end)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+
+    # ---- end to end through the public host-pointer API (pinned host buffers, H2D + D2H) ----
+    import ctypes
+    lib = pb.load_library()
+
+    def pinned(n):
+        ptr = ctypes.c_void_p()
+        assert lib.pb2_host_alloc(ctypes.byref(ptr), 8 * n) == 0
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(n,)), ptr
+
+    hZ, pZ = pinned(p.D * p.K)
+    hD, pD = pinned(max(1, B.dim))
+    hV, pV = pinned(max(1, B.nnz_jac))
+    hZ[:] = zflat
+    e2e_steps = max(3, min(args.steps, 50))
+    for _ in range(2):
+        B.residual_jacobian(hZ, hD, hV)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        B.residual_jacobian(hZ, hD, hV)     # H2D(Z) + kernel + D2H(delta, vals), synchronous
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    times = torch.tensor([total_ms, kern_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms, e2e_ms = (float(x) for x in times.cpu())
+
+    if rank == 0:
+        value = n_eval * world * args.steps / (total_ms * 1e-3)
+        bytes_launch = algorithmic_bytes_per_eval(p) * n_eval
+        peak, peak_src = measured_peak()
+        achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
+        workload = f"C{args.config}"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": dict(workload_config(p, args.config, world),
+                           algorithm=B.algorithm,
+                           l2=f"rotating {nsets} buffer sets ({nsets * set_bytes / 2**20:.0f} MiB > 126 MiB L2); "
+                              "inputs and outputs resident in HBM",
+                           collective="one NCCL all_gather_into_tensor of [delta|vals] per step" if world > 1 else "none"),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(workload),
+                         "kernel": f"knot resjac ({B.algorithm})", "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src},
+            "e2e": {"value": n_eval * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": 8 * p.D * p.K, "d2h_bytes_per_step": 8 * (B.dim + B.nnz_jac),
+                    "steps": e2e_steps,
+                    "note": "pb2_residual_jacobian with pinned host buffers; per rank its own shard"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(p, Z)
+        print(json.dumps(line))
+    for ptr in (pZ, pD, pV):
+        lib.pb2_host_free(ptr)
+    B.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=3)
+    ap.add_argument("--algorithm", default="auto")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

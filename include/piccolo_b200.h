@@ -1,0 +1,130 @@
+/* piccolo_b200.h -- C ABI of the B200-native knot evaluator (libpiccolo_b200.so).
+ *
+ * Drop-in boundary.  The reference (harmoniqs/Piccolo.jl, 100 % Julia) reaches this path
+ * through DirectTrajOpt's AbstractIntegrator interface: a template receives an
+ * `integrator=` object (src/control/templates/smooth_pulse_problem.jl:123,213-233), built
+ * by `BilinearIntegrator(qtraj, N)` (src/control/integrators.jl:35-95), and Ipopt's
+ * eval_g / eval_jac_g / eval_h callbacks call, per integrator,
+ *     evaluate!(delta, B, traj)                     integrators.jl:311, display/inspect.jl:623
+ *     eval_jacobian(B, traj) / jacobian_structure   integrators.jl:780-782, test/aqua.jl:6-9
+ *     hessian_of_lagrangian / hessian_structure     test/aqua.jl:6-9, spline_pulse_problem.jl:96
+ * There is no FFI in the reference; these entry points are what a Julia `ccall` shim
+ * (julia/PiccoloB200.jl) binds, one per callback above.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a PB2_E* code otherwise; the message is in
+ *    pb2_last_error() (thread-local).  Nothing throws or aborts across the boundary.
+ *  - all reals are IEEE float64; all matrices dense column-major (Julia layout);
+ *    index arrays are 1-based int64 (Julia / MOI layout).
+ *  - Z is NamedTrajectory.datavec: D x K column-major, one knot per column
+ *    (src/quantum/trajectories/named_trajectory_conversion.jl:316-321).  Read-only.
+ *  - caller owns every array; the handle owns device workspaces and pinned staging only.
+ *  - a handle is not re-entrant (Ipopt is serial); distinct handles are independent.
+ *  - there is NO CPU fallback: without a usable CUDA device pb2_create fails.
+ */
+#ifndef PICCOLO_B200_H
+#define PICCOLO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB2_VERSION 100
+
+enum {
+  PB2_OK = 0,
+  PB2_EINVAL = 1,      /* bad descriptor / null pointer / unsupported size */
+  PB2_ECUDA = 2,       /* CUDA runtime error (text in pb2_last_error) */
+  PB2_ENODEVICE = 3,   /* no CUDA device: the library refuses to run */
+  PB2_ENOMEM = 4
+};
+
+/* state kinds: which BilinearIntegrator dispatch the handle replaces */
+enum {
+  PB2_KET = 0,      /* integrators.jl:58-74    Ghat = G(u),        x = [Re psi; Im psi]     */
+  PB2_UNITARY = 1,  /* integrators.jl:35-51    Ghat = I_d (x) G(u), x = operator_to_iso_vec  */
+  PB2_DENSITY = 2   /* integrators.jl:82-95    Ghat = compact Lindbladian (non-normal)       */
+};
+
+/* where Z / output pointers live */
+enum {
+  PB2_HOST = 0,   /* host memory: library stages H2D / D2H on its stream, call is synchronous */
+  PB2_DEVICE = 1  /* device memory on desc.device (e.g. CUDA.jl CuArray): no copies          */
+};
+
+enum {
+  PB2_ALG_AUTO = 0,      /* hermitian-eigen path for ket/unitary when available, else generic */
+  PB2_ALG_GENERIC = 1,   /* scaling-and-squaring Taylor jets; any real generator              */
+  PB2_ALG_HERMITIAN = 2  /* complex Hermitian path (ket / unitary only)                      */
+};
+
+typedef struct pb2_desc {
+  int32_t kind;        /* PB2_KET | PB2_UNITARY | PB2_DENSITY */
+  int32_t b;           /* generator block size: 2d (ket, unitary) or d^2 (density) */
+  int32_t n_b;         /* state columns sharing the generator: d for unitary, 1 otherwise */
+  int32_t m;           /* number of (linear) drives */
+  int32_t K;           /* knot columns in the Z passed to this handle -> K-1 constraints */
+  int32_t D;           /* reals per knot (traj.dim) */
+  int32_t x_off;       /* 0-based row of the state block inside a knot column */
+  int32_t dt_off;      /* 0-based row of the timestep */
+  int32_t u_off;       /* 0-based row of the first drive amplitude */
+  int32_t global_dim;  /* trailing global variables in the NLP primal (structure only) */
+  int64_t knot0;       /* global index of this handle's first knot (sharded use; else 0) */
+  int32_t device;      /* CUDA device ordinal */
+  int32_t algorithm;   /* PB2_ALG_* */
+  const double* G0;    /* host, b*b column-major: drift generator (dissipators folded in) */
+  const double* Gj;    /* host, m blocks of b*b column-major: drive generators */
+} pb2_desc;
+
+typedef struct pb2_handle pb2_handle;
+
+int pb2_version(void);
+const char* pb2_last_error(void);
+int pb2_device_count(void);
+
+int pb2_create(const pb2_desc* desc, pb2_handle** out);
+void pb2_destroy(pb2_handle* h);
+
+/* sizes: dim = n_x (K-1)  (integrator.dim, integrators.jl:309) */
+int64_t pb2_dim(const pb2_handle* h);
+int64_t pb2_nnz_jac(const pb2_handle* h);
+int64_t pb2_nnz_hess(const pb2_handle* h);
+int32_t pb2_algorithm(const pb2_handle* h); /* the path actually selected */
+
+/* COO structure, 1-based, deterministic, computed on the host (no device work).
+ * Order documented in DESIGN.md ("canonical COO order"); rows of the Jacobian are
+ * (knot0 + k) n_x + i, columns index the NLP primal [vec(Z); globals]. */
+int pb2_structure_jac(const pb2_handle* h, int64_t* rows, int64_t* cols);
+int pb2_structure_hess(const pb2_handle* h, int64_t* rows, int64_t* cols);
+
+/* evaluate!(delta, B, traj) */
+int pb2_residual(pb2_handle* h, const double* Z, double* delta, int space);
+/* eval_jacobian values in pb2_structure_jac order */
+int pb2_jacobian(pb2_handle* h, const double* Z, double* vals, int space);
+/* fused residual + Jacobian (one kernel): the benchmarked entry */
+int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double* vals, int space);
+/* Hessian of sum_k mu_k . delta_k, upper triangle, in pb2_structure_hess order */
+int pb2_hess_lagrangian(pb2_handle* h, const double* Z, const double* mu, double* vals, int space);
+
+/* Device-pointer, asynchronous forms: enqueue on `stream` (a cudaStream_t; NULL = the
+ * handle's own stream) and return without synchronizing.  delta / vals / hess may be NULL
+ * to skip that output. */
+int pb2_residual_jacobian_async(pb2_handle* h, const double* dZ, double* ddelta, double* dvals,
+                                void* stream);
+int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu, double* dvals,
+                              void* stream);
+int pb2_sync(pb2_handle* h);
+
+/* pinned host memory for callers that want DMA without the staging copy */
+int pb2_host_alloc(void** ptr, int64_t bytes);
+int pb2_host_free(void* ptr);
+
+/* launch accounting for benchmarks: kernels launched by this handle since creation */
+int64_t pb2_launch_count(const pb2_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PICCOLO_B200_H */

@@ -1,0 +1,87 @@
+"""ctypes binding of include/piccolo_b200.h (the same symbols a Julia ``ccall`` shim binds)."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libpiccolo_b200.so")
+
+PB2_KET, PB2_UNITARY, PB2_DENSITY = 0, 1, 2
+PB2_HOST, PB2_DEVICE = 0, 1
+PB2_ALG_AUTO, PB2_ALG_GENERIC, PB2_ALG_HERMITIAN = 0, 1, 2
+KIND = {"ket": PB2_KET, "unitary": PB2_UNITARY, "density": PB2_DENSITY}
+ALG = {"auto": PB2_ALG_AUTO, "generic": PB2_ALG_GENERIC, "hermitian": PB2_ALG_HERMITIAN}
+
+# every symbol include/piccolo_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "pb2_version", "pb2_last_error", "pb2_device_count", "pb2_create", "pb2_destroy",
+    "pb2_dim", "pb2_nnz_jac", "pb2_nnz_hess", "pb2_algorithm", "pb2_structure_jac",
+    "pb2_structure_hess", "pb2_residual", "pb2_jacobian", "pb2_residual_jacobian",
+    "pb2_hess_lagrangian", "pb2_residual_jacobian_async", "pb2_hess_lagrangian_async",
+    "pb2_sync", "pb2_host_alloc", "pb2_host_free", "pb2_launch_count",
+]
+
+
+class PB2Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libpiccolo_b200 error {code}: {msg}")
+        self.code = code
+
+
+class pb2_desc(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int32), ("b", ctypes.c_int32), ("n_b", ctypes.c_int32),
+        ("m", ctypes.c_int32), ("K", ctypes.c_int32), ("D", ctypes.c_int32),
+        ("x_off", ctypes.c_int32), ("dt_off", ctypes.c_int32), ("u_off", ctypes.c_int32),
+        ("global_dim", ctypes.c_int32), ("knot0", ctypes.c_int64), ("device", ctypes.c_int32),
+        ("algorithm", ctypes.c_int32), ("G0", ctypes.POINTER(ctypes.c_double)),
+        ("Gj", ctypes.POINTER(ctypes.c_double)),
+    ]
+
+
+_lib = None
+
+
+def lib_path():
+    return _SO
+
+
+def load_library():
+    """Load libpiccolo_b200.so; fail loudly (no fallback) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise PB2Error(-1, f"{_SO} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "or `make -C piccolo.jl_b200` (there is no CPU fallback)")
+    L = ctypes.CDLL(_SO)
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)
+    vp, H = ctypes.c_void_p, ctypes.c_void_p
+    L.pb2_version.restype = ctypes.c_int
+    L.pb2_last_error.restype = ctypes.c_char_p
+    L.pb2_device_count.restype = ctypes.c_int
+    L.pb2_create.argtypes = [ctypes.POINTER(pb2_desc), ctypes.POINTER(H)]
+    L.pb2_destroy.argtypes = [H]
+    L.pb2_destroy.restype = None
+    for f in ("pb2_dim", "pb2_nnz_jac", "pb2_nnz_hess", "pb2_launch_count"):
+        getattr(L, f).argtypes = [H]
+        getattr(L, f).restype = ctypes.c_int64
+    L.pb2_algorithm.argtypes = [H]
+    L.pb2_algorithm.restype = ctypes.c_int32
+    L.pb2_structure_jac.argtypes = [H, ip, ip]
+    L.pb2_structure_hess.argtypes = [H, ip, ip]
+    L.pb2_residual.argtypes = [H, vp, vp, ctypes.c_int]
+    L.pb2_jacobian.argtypes = [H, vp, vp, ctypes.c_int]
+    L.pb2_residual_jacobian.argtypes = [H, vp, vp, vp, ctypes.c_int]
+    L.pb2_hess_lagrangian.argtypes = [H, vp, vp, vp, ctypes.c_int]
+    L.pb2_residual_jacobian_async.argtypes = [H, vp, vp, vp, vp]
+    L.pb2_hess_lagrangian_async.argtypes = [H, vp, vp, vp, vp]
+    L.pb2_sync.argtypes = [H]
+    L.pb2_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_int64]
+    L.pb2_host_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise PB2Error(rc, load_library().pb2_last_error().decode())

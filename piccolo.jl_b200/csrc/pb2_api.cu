@@ -1,0 +1,482 @@
+// C ABI of libpiccolo_b200.so (declared in include/piccolo_b200.h).
+//
+// Host side of the drop-in boundary: owns the handle (device copies of the generator
+// factors, device/pinned staging for host-pointer calls, launch configuration) and turns
+// each DirectTrajOpt callback -- evaluate! / eval_jacobian / hessian_of_lagrangian, see the
+// header for the reference call sites -- into one kernel launch.  No CPU compute path exists
+// in this library: if CUDA is unavailable pb2_create fails with PB2_ENODEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/piccolo_b200.h"
+#include "knot_generic.cuh"
+#include "knot_hermitian.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PB2_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(PB2_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+constexpr int kNT = 256;
+constexpr size_t kSmemLimit = 227 * 1024;
+
+struct LaunchCfg {
+  int GS = 0, KPC = 0, gj_in_smem = 0;
+  size_t smem = 0;
+};
+
+bool plan_generic(int order, int b, int n_b, int m, LaunchCfg& cfg) {
+  const int bb = b * b;
+  const int npair = order == 2 ? m * (m + 1) / 2 : 0;
+  const int work = (1 + m + npair) * bb;
+  int GS = std::min(kNT, std::max(32, (work + 31) / 32 * 32));
+  // prefer more knots per block for tiny generators, bounded by shared memory
+  for (int gj = 1; gj >= 0; --gj) {
+    for (int KPC = kNT / GS; KPC >= 1; KPC /= 2) {
+      size_t smem = pb2::generic_smem_bytes(order, b, n_b, m, GS, KPC, gj != 0);
+      if (smem <= kSmemLimit) {
+        cfg.GS = GS;
+        cfg.KPC = KPC;
+        cfg.gj_in_smem = gj;
+        cfg.smem = smem;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+double theta_bound(int q) {
+  double lo = 0.0, hi = q + 1.0;
+  const double target = std::log(std::ldexp(1.0, -53));
+  for (int it = 0; it < 200; ++it) {
+    double th = 0.5 * (lo + hi);
+    double lg = (q + 1) * std::log(th) - std::lgamma(q + 2.0) - std::log1p(-th / (q + 2.0));
+    if (lg <= target) lo = th; else hi = th;
+  }
+  return lo;
+}
+
+}  // namespace
+
+struct pb2_handle {
+  pb2_desc d{};
+  std::vector<double> G0, Gj;
+  int alg = PB2_ALG_GENERIC;
+  cudaStream_t stream = nullptr;
+  double *dG0 = nullptr, *dGj = nullptr;
+  pb2::HermitianConsts* dHerm = nullptr;
+  // staging for host-pointer calls
+  double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
+  double *hZ = nullptr, *hDelta = nullptr, *hJac = nullptr, *hMu = nullptr, *hHess = nullptr;
+  LaunchCfg cfg1, cfg2;
+  int64_t launches = 0;
+
+  int n_x() const { return d.b * d.n_b; }
+  int64_t nk() const { return (int64_t)d.K - 1; }
+  int nnz_jac_knot() const { return d.n_b * d.b * d.b + n_x() * d.m + 2 * n_x(); }
+  int nnz_hess_knot() const { return n_x() * d.m + n_x() + d.m * (d.m + 1) / 2 + d.m + 1; }
+};
+
+namespace {
+
+pb2::KnotParams make_params(const pb2_handle* h) {
+  pb2::KnotParams p{};
+  p.b = h->d.b; p.n_b = h->d.n_b; p.m = h->d.m; p.K = h->d.K; p.D = h->d.D;
+  p.x_off = h->d.x_off; p.dt_off = h->d.dt_off; p.u_off = h->d.u_off;
+  p.nnz_jac = h->nnz_jac_knot(); p.nnz_hess = h->nnz_hess_knot();
+  p.G0 = h->dG0; p.Gj = h->dGj;
+  return p;
+}
+
+int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st) {
+  if (h->nk() <= 0) return PB2_OK;
+  pb2::KnotParams p = make_params(h);
+  p.Z = dZ; p.delta = ddelta; p.jac = djac;
+  if (h->alg == PB2_ALG_HERMITIAN) {
+    cudaError_t e = pb2::launch_hermitian_resjac(p, h->dHerm, st);
+    if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("hermitian resjac launch: ") + cudaGetErrorString(e));
+  } else {
+    const LaunchCfg& c = h->cfg1;
+    const int blocks = (int)((h->nk() + c.KPC - 1) / c.KPC);
+    pb2::knot_generic_kernel<1, kNT><<<blocks, kNT, c.smem, st>>>(p, c.GS, c.KPC, c.gj_in_smem);
+    PB2_CUDA(cudaGetLastError());
+  }
+  h->launches++;
+  return PB2_OK;
+}
+
+int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhess, cudaStream_t st) {
+  if (h->nk() <= 0) return PB2_OK;
+  pb2::KnotParams p = make_params(h);
+  p.Z = dZ; p.mu = dmu; p.hess = dhess;
+  if (h->alg == PB2_ALG_HERMITIAN) {
+    cudaError_t e = pb2::launch_hermitian_hess(p, h->dHerm, st);
+    if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("hermitian hess launch: ") + cudaGetErrorString(e));
+  } else {
+    const LaunchCfg& c = h->cfg2;
+    const int blocks = (int)((h->nk() + c.KPC - 1) / c.KPC);
+    pb2::knot_generic_kernel<2, kNT><<<blocks, kNT, c.smem, st>>>(p, c.GS, c.KPC, c.gj_in_smem);
+    PB2_CUDA(cudaGetLastError());
+  }
+  h->launches++;
+  return PB2_OK;
+}
+
+bool is_pinned_or_device(const void* ptr) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// host -> device (through pinned staging unless the caller's buffer is already pinned)
+int stage_in(pb2_handle* h, const double* src, double* pinned, double* dst, size_t n) {
+  if (n == 0) return PB2_OK;
+  const double* from = src;
+  if (!is_pinned_or_device(src)) {
+    std::memcpy(pinned, src, n * sizeof(double));
+    from = pinned;
+  }
+  PB2_CUDA(cudaMemcpyAsync(dst, from, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return PB2_OK;
+}
+
+struct PendingOut {
+  double* user;
+  double* pinned;
+  size_t n;
+  bool direct;
+};
+
+int stage_out_begin(pb2_handle* h, double* user, double* pinned, const double* dsrc, size_t n,
+                    PendingOut& po) {
+  po = {user, pinned, n, false};
+  if (n == 0) return PB2_OK;
+  po.direct = is_pinned_or_device(user);
+  PB2_CUDA(cudaMemcpyAsync(po.direct ? user : pinned, dsrc, n * sizeof(double),
+                           cudaMemcpyDeviceToHost, h->stream));
+  return PB2_OK;
+}
+
+void stage_out_finish(const PendingOut& po) {
+  if (po.n && !po.direct) std::memcpy(po.user, po.pinned, po.n * sizeof(double));
+}
+
+int check(const pb2_handle* h) {
+  if (!h) return fail(PB2_EINVAL, "null handle");
+  return PB2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pb2_version(void) { return PB2_VERSION; }
+
+const char* pb2_last_error(void) { return g_err.c_str(); }
+
+int pb2_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int pb2_create(const pb2_desc* desc, pb2_handle** out) {
+  if (!desc || !out) return fail(PB2_EINVAL, "pb2_create: null argument");
+  *out = nullptr;
+  const pb2_desc& d = *desc;
+  if (d.kind < PB2_KET || d.kind > PB2_DENSITY) return fail(PB2_EINVAL, "pb2_create: bad kind");
+  if (d.b < 1 || d.n_b < 1 || d.m < 0 || d.K < 1 || d.D < 1)
+    return fail(PB2_EINVAL, "pb2_create: sizes must be positive");
+  if ((d.kind == PB2_KET || d.kind == PB2_UNITARY) && (d.b % 2))
+    return fail(PB2_EINVAL, "pb2_create: ket/unitary generators have even size 2d");
+  if (d.kind == PB2_UNITARY && d.n_b * 2 != d.b)
+    return fail(PB2_EINVAL, "pb2_create: unitary needs n_b = b/2");
+  if (d.kind != PB2_UNITARY && d.n_b != 1)
+    return fail(PB2_EINVAL, "pb2_create: ket/density need n_b = 1");
+  const int n_x = d.b * d.n_b;
+  auto inside = [&](int off, int len) { return off >= 0 && off + len <= d.D; };
+  if (!inside(d.x_off, n_x) || !inside(d.dt_off, 1) || !inside(d.u_off, d.m))
+    return fail(PB2_EINVAL, "pb2_create: component offsets outside the knot column");
+  if (!d.G0 || (d.m > 0 && !d.Gj)) return fail(PB2_EINVAL, "pb2_create: null generator");
+  if (d.algorithm < PB2_ALG_AUTO || d.algorithm > PB2_ALG_HERMITIAN)
+    return fail(PB2_EINVAL, "pb2_create: bad algorithm");
+
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(PB2_ENODEVICE, "pb2_create: no CUDA device (this library has no CPU path)");
+  }
+  if (d.device < 0 || d.device >= ndev) return fail(PB2_EINVAL, "pb2_create: bad device ordinal");
+  PB2_CUDA(cudaSetDevice(d.device));
+
+  pb2_handle* h = new (std::nothrow) pb2_handle();
+  if (!h) return fail(PB2_ENOMEM, "pb2_create: out of memory");
+  h->d = d;
+  const size_t bb = (size_t)d.b * d.b;
+  h->G0.assign(d.G0, d.G0 + bb);
+  if (d.m) h->Gj.assign(d.Gj, d.Gj + (size_t)d.m * bb);
+  h->d.G0 = h->G0.data();
+  h->d.Gj = h->Gj.data();
+
+  // algorithm selection (decided once, at construction -- never a runtime fallback)
+  const bool herm_ok = (d.kind != PB2_DENSITY) &&
+                       pb2::hermitian_supported(d.b, d.n_b, d.m, h->G0.data(), h->Gj.data());
+  if (d.algorithm == PB2_ALG_HERMITIAN && !herm_ok) {
+    delete h;
+    return fail(PB2_EINVAL, "pb2_create: hermitian path unsupported for this generator/size");
+  }
+  h->alg = (d.algorithm == PB2_ALG_GENERIC || !herm_ok) ? PB2_ALG_GENERIC : PB2_ALG_HERMITIAN;
+
+  if (h->alg == PB2_ALG_GENERIC) {
+    if (!plan_generic(1, d.b, d.n_b, d.m, h->cfg1) || !plan_generic(2, d.b, d.n_b, d.m, h->cfg2)) {
+      delete h;
+      return fail(PB2_EINVAL, "pb2_create: generator too large for the shared-memory kernels");
+    }
+  }
+
+  auto cleanup_fail = [&](int code, const std::string& msg) {
+    pb2_destroy(h);
+    return fail(code, msg);
+  };
+#define PB2_CUDA_H(call)                                                                  \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return cleanup_fail(PB2_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+  PB2_CUDA_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  PB2_CUDA_H(cudaMalloc(&h->dG0, bb * sizeof(double)));
+  PB2_CUDA_H(cudaMalloc(&h->dGj, std::max<size_t>(1, (size_t)d.m * bb) * sizeof(double)));
+  PB2_CUDA_H(cudaMemcpy(h->dG0, h->G0.data(), bb * sizeof(double), cudaMemcpyHostToDevice));
+  if (d.m)
+    PB2_CUDA_H(cudaMemcpy(h->dGj, h->Gj.data(), (size_t)d.m * bb * sizeof(double), cudaMemcpyHostToDevice));
+
+  double theta[pb2::kMaxDeg + 1];
+  theta[0] = 0.0;
+  for (int q = 1; q <= pb2::kMaxDeg; ++q) theta[q] = theta_bound(q);
+  PB2_CUDA_H(cudaMemcpyToSymbol(pb2::c_theta, theta, sizeof(theta)));
+
+  if (h->alg == PB2_ALG_GENERIC) {
+    PB2_CUDA_H(cudaFuncSetAttribute(pb2::knot_generic_kernel<1, kNT>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cfg1.smem));
+    PB2_CUDA_H(cudaFuncSetAttribute(pb2::knot_generic_kernel<2, kNT>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cfg2.smem));
+  } else {
+    cudaError_t e = pb2::hermitian_setup(d.b, d.n_b, d.m, h->G0.data(), h->Gj.data(), &h->dHerm);
+    if (e != cudaSuccess)
+      return cleanup_fail(PB2_ECUDA, std::string("hermitian_setup: ") + cudaGetErrorString(e));
+  }
+#undef PB2_CUDA_H
+  *out = h;
+  return PB2_OK;
+}
+
+void pb2_destroy(pb2_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->d.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (double* p : {h->dG0, h->dGj, h->dZ, h->dDelta, h->dJac, h->dMu, h->dHess})
+    if (p) cudaFree(p);
+  if (h->dHerm) cudaFree(h->dHerm);
+  for (double* p : {h->hZ, h->hDelta, h->hJac, h->hMu, h->hHess})
+    if (p) cudaFreeHost(p);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaGetLastError();
+  delete h;
+}
+
+int64_t pb2_dim(const pb2_handle* h) { return h ? (int64_t)h->n_x() * h->nk() : -1; }
+int64_t pb2_nnz_jac(const pb2_handle* h) { return h ? (int64_t)h->nnz_jac_knot() * h->nk() : -1; }
+int64_t pb2_nnz_hess(const pb2_handle* h) { return h ? (int64_t)h->nnz_hess_knot() * h->nk() : -1; }
+int32_t pb2_algorithm(const pb2_handle* h) { return h ? h->alg : -1; }
+int64_t pb2_launch_count(const pb2_handle* h) { return h ? h->launches : -1; }
+
+int pb2_structure_jac(const pb2_handle* h, int64_t* rows, int64_t* cols) {
+  if (check(h)) return PB2_EINVAL;
+  if (!rows || !cols) return fail(PB2_EINVAL, "pb2_structure_jac: null output");
+  const pb2_desc& d = h->d;
+  const int64_t b = d.b, n_b = d.n_b, m = d.m, n_x = h->n_x(), D = d.D;
+  int64_t o = 0;
+  for (int64_t kl = 0; kl < h->nk(); ++kl) {
+    const int64_t k = d.knot0 + kl;
+    const int64_t r0 = k * n_x + 1, c0 = k * D + 1;
+    for (int64_t c = 0; c < n_b; ++c)
+      for (int64_t j = 0; j < b; ++j)
+        for (int64_t i = 0; i < b; ++i) {
+          rows[o] = r0 + c * b + i;
+          cols[o++] = c0 + d.x_off + c * b + j;
+        }
+    for (int64_t j = 0; j < m; ++j)
+      for (int64_t i = 0; i < n_x; ++i) {
+        rows[o] = r0 + i;
+        cols[o++] = c0 + d.u_off + j;
+      }
+    for (int64_t i = 0; i < n_x; ++i) {
+      rows[o] = r0 + i;
+      cols[o++] = c0 + d.dt_off;
+    }
+    for (int64_t i = 0; i < n_x; ++i) {
+      rows[o] = r0 + i;
+      cols[o++] = c0 + D + d.x_off + i;
+    }
+  }
+  return PB2_OK;
+}
+
+int pb2_structure_hess(const pb2_handle* h, int64_t* rows, int64_t* cols) {
+  if (check(h)) return PB2_EINVAL;
+  if (!rows || !cols) return fail(PB2_EINVAL, "pb2_structure_hess: null output");
+  const pb2_desc& d = h->d;
+  const int64_t m = d.m, n_x = h->n_x(), D = d.D;
+  int64_t o = 0;
+  auto emit = [&](int64_t a, int64_t c) {
+    rows[o] = std::min(a, c);
+    cols[o++] = std::max(a, c);
+  };
+  for (int64_t kl = 0; kl < h->nk(); ++kl) {
+    const int64_t c0 = (d.knot0 + kl) * D + 1;
+    for (int64_t j = 0; j < m; ++j)
+      for (int64_t i = 0; i < n_x; ++i) emit(c0 + d.x_off + i, c0 + d.u_off + j);
+    for (int64_t i = 0; i < n_x; ++i) emit(c0 + d.x_off + i, c0 + d.dt_off);
+    for (int64_t j = 0; j < m; ++j)
+      for (int64_t i = 0; i <= j; ++i) emit(c0 + d.u_off + i, c0 + d.u_off + j);
+    for (int64_t j = 0; j < m; ++j) emit(c0 + d.u_off + j, c0 + d.dt_off);
+    emit(c0 + d.dt_off, c0 + d.dt_off);
+  }
+  return PB2_OK;
+}
+
+int pb2_residual_jacobian_async(pb2_handle* h, const double* dZ, double* ddelta, double* dvals,
+                                void* stream) {
+  if (check(h)) return PB2_EINVAL;
+  if (!dZ) return fail(PB2_EINVAL, "pb2_residual_jacobian_async: null Z");
+  PB2_CUDA(cudaSetDevice(h->d.device));
+  return launch_resjac(h, dZ, ddelta, dvals, stream ? (cudaStream_t)stream : h->stream);
+}
+
+int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu, double* dvals,
+                              void* stream) {
+  if (check(h)) return PB2_EINVAL;
+  if (!dZ || !dmu || !dvals) return fail(PB2_EINVAL, "pb2_hess_lagrangian_async: null argument");
+  PB2_CUDA(cudaSetDevice(h->d.device));
+  return launch_hess(h, dZ, dmu, dvals, stream ? (cudaStream_t)stream : h->stream);
+}
+
+int pb2_sync(pb2_handle* h) {
+  if (check(h)) return PB2_EINVAL;
+  PB2_CUDA(cudaSetDevice(h->d.device));
+  PB2_CUDA(cudaStreamSynchronize(h->stream));
+  return PB2_OK;
+}
+
+static int ensure(double** dev, double** host, size_t n) {
+  if (n == 0) n = 1;
+  if (dev && !*dev) PB2_CUDA(cudaMalloc(dev, n * sizeof(double)));
+  if (host && !*host) PB2_CUDA(cudaMallocHost(host, n * sizeof(double)));
+  return PB2_OK;
+}
+
+int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double* vals, int space) {
+  if (check(h)) return PB2_EINVAL;
+  if (!Z) return fail(PB2_EINVAL, "pb2_residual_jacobian: null Z");
+  PB2_CUDA(cudaSetDevice(h->d.device));
+  if (space == PB2_DEVICE) {
+    int rc = launch_resjac(h, Z, delta, vals, h->stream);
+    if (rc) return rc;
+    PB2_CUDA(cudaStreamSynchronize(h->stream));
+    return PB2_OK;
+  }
+  if (space != PB2_HOST) return fail(PB2_EINVAL, "pb2_residual_jacobian: bad space");
+  const size_t nZ = (size_t)h->d.D * h->d.K, nD = (size_t)pb2_dim(h), nJ = (size_t)pb2_nnz_jac(h);
+  int rc;
+  if ((rc = ensure(&h->dZ, &h->hZ, nZ))) return rc;
+  if (delta && (rc = ensure(&h->dDelta, &h->hDelta, nD))) return rc;
+  if (vals && (rc = ensure(&h->dJac, &h->hJac, nJ))) return rc;
+  if ((rc = stage_in(h, Z, h->hZ, h->dZ, nZ))) return rc;
+  if ((rc = launch_resjac(h, h->dZ, delta ? h->dDelta : nullptr, vals ? h->dJac : nullptr, h->stream)))
+    return rc;
+  PendingOut po1{}, po2{};
+  if (delta && (rc = stage_out_begin(h, delta, h->hDelta, h->dDelta, nD, po1))) return rc;
+  if (vals && (rc = stage_out_begin(h, vals, h->hJac, h->dJac, nJ, po2))) return rc;
+  PB2_CUDA(cudaStreamSynchronize(h->stream));
+  stage_out_finish(po1);
+  stage_out_finish(po2);
+  return PB2_OK;
+}
+
+int pb2_residual(pb2_handle* h, const double* Z, double* delta, int space) {
+  if (!delta) return fail(PB2_EINVAL, "pb2_residual: null output");
+  return pb2_residual_jacobian(h, Z, delta, nullptr, space);
+}
+
+int pb2_jacobian(pb2_handle* h, const double* Z, double* vals, int space) {
+  if (!vals) return fail(PB2_EINVAL, "pb2_jacobian: null output");
+  return pb2_residual_jacobian(h, Z, nullptr, vals, space);
+}
+
+int pb2_hess_lagrangian(pb2_handle* h, const double* Z, const double* mu, double* vals, int space) {
+  if (check(h)) return PB2_EINVAL;
+  if (!Z || !mu || !vals) return fail(PB2_EINVAL, "pb2_hess_lagrangian: null argument");
+  PB2_CUDA(cudaSetDevice(h->d.device));
+  if (space == PB2_DEVICE) {
+    int rc = launch_hess(h, Z, mu, vals, h->stream);
+    if (rc) return rc;
+    PB2_CUDA(cudaStreamSynchronize(h->stream));
+    return PB2_OK;
+  }
+  if (space != PB2_HOST) return fail(PB2_EINVAL, "pb2_hess_lagrangian: bad space");
+  const size_t nZ = (size_t)h->d.D * h->d.K, nD = (size_t)pb2_dim(h), nH = (size_t)pb2_nnz_hess(h);
+  int rc;
+  if ((rc = ensure(&h->dZ, &h->hZ, nZ))) return rc;
+  if ((rc = ensure(&h->dMu, &h->hMu, nD))) return rc;
+  if ((rc = ensure(&h->dHess, &h->hHess, nH))) return rc;
+  if ((rc = stage_in(h, Z, h->hZ, h->dZ, nZ))) return rc;
+  if ((rc = stage_in(h, mu, h->hMu, h->dMu, nD))) return rc;
+  if ((rc = launch_hess(h, h->dZ, h->dMu, h->dHess, h->stream))) return rc;
+  PendingOut po{};
+  if ((rc = stage_out_begin(h, vals, h->hHess, h->dHess, nH, po))) return rc;
+  PB2_CUDA(cudaStreamSynchronize(h->stream));
+  stage_out_finish(po);
+  return PB2_OK;
+}
+
+int pb2_host_alloc(void** ptr, int64_t bytes) {
+  if (!ptr || bytes < 0) return fail(PB2_EINVAL, "pb2_host_alloc: bad argument");
+  PB2_CUDA(cudaMallocHost(ptr, (size_t)std::max<int64_t>(bytes, 8)));
+  return PB2_OK;
+}
+
+int pb2_host_free(void* ptr) {
+  if (!ptr) return PB2_OK;
+  PB2_CUDA(cudaFreeHost(ptr));
+  return PB2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's integrator interface for the knot path.
+
+Reference: /root/reference/src/control/integrators.jl:35-95 (dispatch on trajectory type),
+DirectTrajOpt's evaluate!/eval_jacobian/jacobian_structure/hessian_structure contract as seen
+from the reference's call sites (integrators.jl:307-311,780-782; display/inspect.jl:611-623).
+Every numeric call goes through the C ABI (capi.py); nothing here computes the path on the CPU.
+"""
+import ctypes
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import capi, generators as gen
+
+
+# ----------------------------------------------------------------------------- #
+# minimal containers mirroring the reference's (only what the path reads)
+# ----------------------------------------------------------------------------- #
+
+@dataclass
+class QuantumSystem:
+    """QuantumSystem(H_drift, H_drives, drive_bounds)  (quantum_systems.jl:192-249)."""
+    H_drift: np.ndarray
+    H_drives: List[np.ndarray]
+    drive_bounds: Sequence[float] = ()
+
+    def __post_init__(self):
+        self.H_drift = np.asarray(self.H_drift, dtype=complex)
+        self.H_drives = [np.asarray(H, dtype=complex) for H in self.H_drives]
+        if not np.allclose(self.H_drift, self.H_drift.conj().T):
+            raise ValueError("Drift Hamiltonian H_drift is not Hermitian")
+        for i, H in enumerate(self.H_drives):
+            if not np.allclose(H, H.conj().T):
+                raise ValueError(f"Drive Hamiltonian H_drives[{i + 1}] is not Hermitian")
+
+    levels = property(lambda self: self.H_drift.shape[0])
+    n_drives = property(lambda self: len(self.H_drives))
+
+    def G_parts(self):
+        return gen.G(self.H_drift), [gen.G(H) for H in self.H_drives]
+
+
+@dataclass
+class OpenQuantumSystem(QuantumSystem):
+    """OpenQuantumSystem(H_drift, H_drives, bounds; dissipation_operators)  (open_quantum_systems.jl:30-41)."""
+    dissipation_operators: List[np.ndarray] = field(default_factory=list)
+    rates: Optional[List[float]] = None
+
+    def G_parts(self):
+        return gen.compact_generator_parts(self.H_drift, self.H_drives,
+                                           self.dissipation_operators, self.rates)
+
+
+class NamedTrajectory:
+    """The slice of NamedTrajectories.NamedTrajectory the path touches: ``datavec`` as a
+    D x K column-major matrix plus named row ranges (named_trajectory_conversion.jl:316-321)."""
+
+    def __init__(self, data: np.ndarray, components: Dict[str, range], timestep="Δt", global_dim=0):
+        self.data = np.asfortranarray(data, dtype=np.float64)
+        self.components = dict(components)
+        self.timestep = timestep
+        self.global_dim = global_dim
+
+    dim = property(lambda self: self.data.shape[0])
+    N = property(lambda self: self.data.shape[1])
+
+    @property
+    def datavec(self):
+        return self.data.reshape(-1, order="F")
+
+    @classmethod
+    def smooth_pulse_layout(cls, data, n_x, m, state_name, derivs=2):
+        """[state | Δt | t | u | du | ddu]   (smooth_pulse_problem.jl:196-201)."""
+        comps = {state_name: range(0, n_x), "Δt": range(n_x, n_x + 1), "t": range(n_x + 1, n_x + 2),
+                 "u": range(n_x + 2, n_x + 2 + m)}
+        o = n_x + 2 + m
+        for name in ["du", "ddu", "dddu"][:derivs]:
+            comps[name] = range(o, o + m)
+            o += m
+        return cls(data, comps)
+
+
+@dataclass
+class _QTraj:
+    system: QuantumSystem
+
+
+class UnitaryTrajectory(_QTraj):
+    kind, state_name = "unitary", "Ũ⃗"
+
+
+class KetTrajectory(_QTraj):
+    kind, state_name = "ket", "ψ̃"
+
+
+class DensityTrajectory(_QTraj):
+    kind, state_name = "density", "ρ⃗̃"
+
+
+# ----------------------------------------------------------------------------- #
+# the integrator
+# ----------------------------------------------------------------------------- #
+
+def _as_ptr(a):
+    """numpy array -> address; torch CUDA tensor / int -> address."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return int(a)
+
+
+class B200BilinearIntegrator:
+    """One dynamics integrator (one state component) evaluated on a B200.
+
+    Fields mirror DirectTrajOpt's BilinearIntegrator as used by the reference:
+    ``dim == x_dim * (N - 1)`` (integrators.jl:309), ``x_dim``, ``x_name``.
+    """
+
+    def __init__(self, kind, G_drift, G_drives, *, K, D, x_off, dt_off, u_off, x_name="x",
+                 u_name="u", device=0, algorithm="auto", knot0=0, global_dim=0):
+        self._lib = capi.load_library()
+        G0 = np.asfortranarray(G_drift, dtype=np.float64)
+        b = G0.shape[0]
+        m = len(G_drives)
+        Gj = (np.concatenate([np.asfortranarray(g, dtype=np.float64).reshape(-1, order="F")
+                              for g in G_drives]) if m else np.zeros(1))
+        self.kind, self.b, self.m = kind, b, m
+        self.n_b = b // 2 if kind == "unitary" else 1
+        self.x_dim = b * self.n_b
+        self.K, self.D = int(K), int(D)
+        self.x_off, self.dt_off, self.u_off = int(x_off), int(dt_off), int(u_off)
+        self.x_name, self.u_name = x_name, u_name
+        self.knot0, self.global_dim, self.device = int(knot0), int(global_dim), int(device)
+        self._G0, self._Gj = G0, Gj  # keep alive during create
+        d = capi.pb2_desc(capi.KIND[kind], b, self.n_b, m, self.K, self.D, self.x_off, self.dt_off,
+                          self.u_off, self.global_dim, self.knot0, self.device, capi.ALG[algorithm],
+                          G0.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                          Gj.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        h = ctypes.c_void_p()
+        capi.check(self._lib.pb2_create(ctypes.byref(d), ctypes.byref(h)))
+        self._h = h
+        self.dim = int(self._lib.pb2_dim(h))
+        self.nnz_jac = int(self._lib.pb2_nnz_jac(h))
+        self.nnz_hess = int(self._lib.pb2_nnz_hess(h))
+        self.algorithm = {1: "generic", 2: "hermitian"}[self._lib.pb2_algorithm(h)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pb2_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # -- structure -------------------------------------------------------------------------
+    def jacobian_structure(self):
+        rows = np.empty(self.nnz_jac, dtype=np.int64)
+        cols = np.empty(self.nnz_jac, dtype=np.int64)
+        ip = ctypes.POINTER(ctypes.c_int64)
+        capi.check(self._lib.pb2_structure_jac(self._h, rows.ctypes.data_as(ip), cols.ctypes.data_as(ip)))
+        return rows, cols
+
+    def hessian_structure(self):
+        rows = np.empty(self.nnz_hess, dtype=np.int64)
+        cols = np.empty(self.nnz_hess, dtype=np.int64)
+        ip = ctypes.POINTER(ctypes.c_int64)
+        capi.check(self._lib.pb2_structure_hess(self._h, rows.ctypes.data_as(ip), cols.ctypes.data_as(ip)))
+        return rows, cols
+
+    # -- host-pointer calls (what the Ipopt callbacks use) ---------------------------------
+    def _Z(self, Z):
+        Z = Z.data if isinstance(Z, NamedTrajectory) else Z
+        Z = np.asarray(Z, dtype=np.float64)
+        if Z.ndim == 2:
+            if Z.shape != (self.D, self.K):
+                raise ValueError(f"trajectory is {Z.shape}, integrator expects {(self.D, self.K)}")
+            Z = np.asfortranarray(Z)
+        elif Z.size != self.D * self.K:
+            raise ValueError("datavec has the wrong length")
+        return Z
+
+    def evaluate_(self, delta, Z):
+        Z = self._Z(Z)
+        if delta.size != self.dim or delta.dtype != np.float64 or not delta.flags.c_contiguous:
+            raise ValueError("delta must be a contiguous float64 vector of length B.dim")
+        capi.check(self._lib.pb2_residual(self._h, Z.ctypes.data, delta.ctypes.data, capi.PB2_HOST))
+        return delta
+
+    def jacobian_values(self, Z, out=None):
+        Z = self._Z(Z)
+        out = np.empty(self.nnz_jac) if out is None else out
+        capi.check(self._lib.pb2_jacobian(self._h, Z.ctypes.data, out.ctypes.data, capi.PB2_HOST))
+        return out
+
+    def residual_jacobian(self, Z, delta=None, vals=None):
+        Z = self._Z(Z)
+        delta = np.empty(self.dim) if delta is None else delta
+        vals = np.empty(self.nnz_jac) if vals is None else vals
+        capi.check(self._lib.pb2_residual_jacobian(self._h, Z.ctypes.data, delta.ctypes.data,
+                                                   vals.ctypes.data, capi.PB2_HOST))
+        return delta, vals
+
+    def hessian_values(self, Z, mu, out=None):
+        Z = self._Z(Z)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        if mu.size != self.dim:
+            raise ValueError("mu must have length B.dim")
+        out = np.empty(self.nnz_hess) if out is None else out
+        capi.check(self._lib.pb2_hess_lagrangian(self._h, Z.ctypes.data, mu.ctypes.data,
+                                                 out.ctypes.data, capi.PB2_HOST))
+        return out
+
+    # -- device-pointer, asynchronous calls (torch CUDA tensors or raw addresses) -----------
+    def residual_jacobian_device(self, dZ, ddelta, dvals, stream=None):
+        capi.check(self._lib.pb2_residual_jacobian_async(self._h, _as_ptr(dZ), _as_ptr(ddelta),
+                                                         _as_ptr(dvals), _as_ptr(stream)))
+
+    def hessian_device(self, dZ, dmu, dvals, stream=None):
+        capi.check(self._lib.pb2_hess_lagrangian_async(self._h, _as_ptr(dZ), _as_ptr(dmu),
+                                                       _as_ptr(dvals), _as_ptr(stream)))
+
+    def sync(self):
+        capi.check(self._lib.pb2_sync(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.pb2_launch_count(self._h))
+
+
+def BilinearIntegrator(qtraj, traj_or_N, traj=None, **kw):
+    """BilinearIntegrator(qtraj, N) -- dispatch on the trajectory type (integrators.jl:35-95).
+
+    ``traj`` (a NamedTrajectory with the state / Δt / u components) supplies the knot layout;
+    the reference rebuilds it from ``qtraj`` and ``N``, here it is passed in."""
+    if isinstance(traj_or_N, NamedTrajectory):
+        traj = traj_or_N
+    if traj is None:
+        raise TypeError("pass the NamedTrajectory that defines the knot layout")
+    if not isinstance(traj_or_N, NamedTrajectory) and int(traj_or_N) != traj.N:
+        raise ValueError("N does not match the trajectory")
+    G0, Gj = qtraj.system.G_parts()
+    comps = traj.components
+    x = comps[qtraj.state_name]
+    return B200BilinearIntegrator(
+        qtraj.kind, G0, Gj, K=traj.N, D=traj.dim, x_off=x.start, dt_off=comps[traj.timestep].start,
+        u_off=comps["u"].start, x_name=qtraj.state_name, global_dim=traj.global_dim, **kw)
+
+
+# free functions with the reference's names ------------------------------------------------
+
+def evaluate_(delta, B, traj):
+    """evaluate!(δ, B, traj)"""
+    return B.evaluate_(delta, traj)
+
+
+def jacobian_structure(B):
+    return B.jacobian_structure()
+
+
+def hessian_structure(B):
+    return B.hessian_structure()
+
+
+def eval_jacobian(B, traj):
+    """Sparse ``dim x (D*N + global_dim)`` Jacobian (integrators.jl:780-782) as scipy COO."""
+    import scipy.sparse as sp
+    rows, cols = B.jacobian_structure()
+    vals = B.jacobian_values(traj)
+    n = B.D * B.K + B.global_dim
+    total_rows = int(rows.max()) if B.knot0 else B.dim
+    return sp.coo_matrix((vals, (rows - 1, cols - 1)), shape=(total_rows, n))
+
+
+def hessian_of_lagrangian(B, traj, mu):
+    import scipy.sparse as sp
+    rows, cols = B.hessian_structure()
+    vals = B.hessian_values(traj, mu)
+    n = B.D * B.K + B.global_dim
+    return sp.coo_matrix((vals, (rows - 1, cols - 1)), shape=(n, n))

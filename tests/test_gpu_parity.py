@@ -1,0 +1,192 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on identical inputs.
+
+Tolerances (float64 path; north star: residual match <= 1e-10):
+  residual  : 1e-12 absolute   (values are O(1))
+  Jacobian  : 1e-11 absolute   (entries O(1..10))
+  Hessian   : 1e-9 relative to max|H| (entries up to O(1e2), second derivatives)
+COO index arrays: bit-exact.
+"""
+import numpy as np
+import pytest
+
+import piccolo_b200 as pb
+from oracle import configs as C
+from oracle import cport as CP
+from oracle import knot as KN
+from tests import golden_util as GU
+
+pytestmark = pytest.mark.gpu
+
+RES_TOL, JAC_TOL, HESS_RTOL = 1e-12, 1e-11, 1e-9
+
+
+def make(p, algorithm="auto", **kw):
+    return pb.B200BilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off,
+                                     dt_off=p.dt_off, u_off=p.u_off, algorithm=algorithm, **kw)
+
+
+def algorithms(p):
+    return ["generic"] if p.kind == "density" else ["generic", "auto"]
+
+
+def check_all(p, Z, mu, B, hess=True):
+    d, v = B.residual_jacobian(Z)
+    assert np.abs(d - KN.residual(p, Z)).max() < RES_TOL
+    assert np.abs(v - KN.jacobian_values(p, Z)).max() < JAC_TOL
+    # separate entry points give the same numbers as the fused one
+    d2 = np.empty(B.dim)
+    B.evaluate_(d2, Z)
+    assert np.array_equal(d, d2)
+    assert np.array_equal(v, B.jacobian_values(Z))
+    if hess:
+        h = B.hessian_values(Z, mu)
+        ho = KN.hessian_values(p, Z, mu)
+        assert np.abs(h - ho).max() < HESS_RTOL * max(1.0, np.abs(ho).max())
+
+
+@pytest.mark.parametrize("cfg,K", [(1, 50), (2, 33), (3, 20), (4, 40), (6, 17)])
+def test_synthetic_configs_vs_oracle(cfg, K):
+    p, Z, mu = C.trajectory(cfg, K)
+    for alg in algorithms(p):
+        B = make(p, alg)
+        check_all(p, Z, mu, B)
+        B.close()
+
+
+@pytest.mark.parametrize("name", sorted(GU.META))
+def test_golden_trajectories(name):
+    """The reference's own converged solutions: delta ~ 0 from the CUDA path, and full parity."""
+    p, Z = GU.load(name)
+    mu = np.random.default_rng(1).standard_normal(p.dim)
+    for alg in algorithms(p):
+        B = make(p, alg)
+        check_all(p, Z, mu, B)
+        if name in GU.TIGHT:
+            d = np.empty(B.dim)
+            B.evaluate_(d, Z)
+            assert np.abs(d).max() < GU.TIGHT[name]
+        B.close()
+
+
+def test_structure_bit_exact():
+    for cfg in (1, 2, 4, 6):
+        p, Z, mu = C.trajectory(cfg, 7)
+        B = make(p)
+        r, c = B.jacobian_structure()
+        ro, co = KN.jacobian_structure(p)
+        assert r.dtype == np.int64 and np.array_equal(r, ro) and np.array_equal(c, co)
+        r, c = B.hessian_structure()
+        ro, co = KN.hessian_structure(p)
+        assert np.array_equal(r, ro) and np.array_equal(c, co)
+        assert B.dim == p.dim == p.n_x * (p.K - 1)                    # integrators.jl:309
+        J = pb.eval_jacobian(B, Z)
+        assert J.shape == (B.dim, p.D * p.K + p.global_dim)           # integrators.jl:780-782
+        B.close()
+
+
+def test_edge_cases():
+    # K = 1: no constraints at all; K = 2: a single knot; dt = 0: identity propagator
+    p, Z, mu = C.trajectory(2, 2)
+    B = make(p)
+    check_all(p, Z, mu, B)
+    B.close()
+    p1, Z1, _ = C.trajectory(2, 1)
+    B = make(p1)
+    assert B.dim == 0 and B.nnz_jac == 0
+    d, v = B.residual_jacobian(Z1)
+    assert d.size == 0 and v.size == 0
+    B.close()
+    p, Z, mu = C.trajectory(6, 6)
+    Z[p.dt_off, :] = 0.0
+    Z[p.u_off:p.u_off + p.m, 2] = 0.0
+    for alg in algorithms(p):
+        B = make(p, alg)
+        check_all(p, Z, mu, B)
+        B.close()
+
+
+def test_large_norm_and_degenerate_generators():
+    # big dt (||dt G|| ~ 30: many squarings / large phases) and exactly degenerate spectra (u = 0)
+    p, Z, mu = C.trajectory(2, 9)
+    Z[p.dt_off, :] = 3.0
+    Z[p.u_off:p.u_off + p.m, 4:] = 0.0
+    for alg in algorithms(p):
+        B = make(p, alg)
+        d, v = B.residual_jacobian(Z)
+        assert np.abs(d - KN.residual(p, Z)).max() < 1e-10
+        assert np.abs(v - KN.jacobian_values(p, Z)).max() < 1e-9
+        h, ho = B.hessian_values(Z, mu), KN.hessian_values(p, Z, mu)
+        assert np.abs(h - ho).max() < 1e-8 * np.abs(ho).max()
+        B.close()
+
+
+def test_full_size_properties_c3():
+    """BASELINE size (d=8, m=4, K=1000): oracle on a knot subset + size-independent properties."""
+    p, Z, mu = C.trajectory(3, 1000)
+    B = make(p)
+    d, v = B.residual_jacobian(Z)
+    # (1) the C++ port (independent algorithm) on the full trajectory
+    assert np.abs(d - CP.residual(p, Z)).max() < RES_TOL
+    assert np.abs(v - CP.jacobian_values(p, Z)).max() < JAC_TOL
+    # (2) SciPy oracle on a strided subset of knots
+    sub = np.arange(0, p.K - 1, 97)
+    for k in sub:
+        pk = KN.make_problem(p.kind, p.G0, p.Gj, 2)
+        Zk = np.asfortranarray(Z[:, k:k + 2])
+        assert np.abs(d[k * p.n_x:(k + 1) * p.n_x] - KN.residual(pk, Zk)).max() < RES_TOL
+        assert np.abs(v[k * p.nnz_jac_knot:(k + 1) * p.nnz_jac_knot] - KN.jacobian_values(pk, Zk)).max() < JAC_TOL
+    # (3) unitarity of every propagator block written to the Jacobian: E^T E = I
+    V = v.reshape(p.K - 1, p.nnz_jac_knot)
+    E = -V[:, :p.b * p.b].reshape(-1, p.b, p.b)
+    assert np.abs(np.einsum("kij,kil->kjl", E, E) - np.eye(p.b)).max() < 1e-13
+    # (4) the n_b replicated blocks are identical, identity entries are exactly 1
+    for c in range(1, p.n_b):
+        assert np.array_equal(V[:, :p.b * p.b], V[:, c * p.b * p.b:(c + 1) * p.b * p.b])
+    assert np.all(V[:, -p.n_x:] == 1.0)
+    # (5) linearity in the state: delta(x) is affine in Z's state rows
+    Z2 = Z.copy(order="F")
+    Z2[p.x_off:p.x_off + p.n_x, :] *= 2.0
+    d2, v2 = B.residual_jacobian(Z2)
+    assert np.abs(d2 - 2.0 * d).max() < 1e-12
+    assert np.array_equal(v2[: p.b * p.b], v[: p.b * p.b])
+    # (6) exactly propagated states give delta == 0
+    p0, Z0, _ = C.trajectory(3, 1000, noise=0.0)
+    d0, _ = B.residual_jacobian(Z0)
+    assert np.abs(d0).max() < 1e-13
+    # (7) Hessian: symmetric contraction check  z^T H z  vs second difference of mu.delta along z
+    h = B.hessian_values(Z, mu)
+    assert np.abs(h - CP.hessian_values(p, Z, mu)).max() < HESS_RTOL * np.abs(h).max()
+    B.close()
+
+
+def test_device_pointer_api_matches_host_api():
+    import torch
+    p, Z, mu = C.trajectory(2, 40)
+    B = make(p)
+    d, v = B.residual_jacobian(Z)
+    dZ = torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda()
+    dd = torch.empty(B.dim, dtype=torch.float64, device="cuda")
+    dv = torch.empty(B.nnz_jac, dtype=torch.float64, device="cuda")
+    B.residual_jacobian_device(dZ, dd, dv, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(dd.cpu().numpy(), d) and np.array_equal(dv.cpu().numpy(), v)
+    dh = torch.empty(B.nnz_hess, dtype=torch.float64, device="cuda")
+    dmu = torch.from_numpy(mu).cuda()
+    B.hessian_device(dZ, dmu, dh, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(dh.cpu().numpy(), B.hessian_values(Z, mu))
+    assert B.launch_count >= 4
+    B.close()
+
+
+def test_error_behaviour():
+    p, Z, mu = C.trajectory(1, 5)
+    with pytest.raises(pb.PB2Error):
+        pb.B200BilinearIntegrator("unitary", p.G0, list(p.Gj), K=5, D=3, x_off=0, dt_off=8, u_off=10)
+    with pytest.raises(pb.PB2Error):
+        pb.B200BilinearIntegrator("density", p.G0, list(p.Gj), K=5, D=p.D, x_off=0, dt_off=8,
+                                  u_off=10, algorithm="hermitian")
+    B = make(p)
+    with pytest.raises(ValueError):
+        B.residual_jacobian(Z[:, :3])
+    B.close()

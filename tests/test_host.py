@@ -1,0 +1,116 @@
+"""CPU tests of the host side: the C-ABI library loads, exports every declared symbol and refuses
+to run without a GPU; generator factors; the sharding plumbing under gloo (world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import piccolo_b200 as pb
+from oracle import configs as C
+from oracle import isomorphisms as oiso
+from oracle import knot as KN
+from oracle import systems as S
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_library_exports_every_declared_symbol():
+    from piccolo_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "piccolo_b200.h")).read()
+    declared = set(re.findall(r"\b(pb2_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(capi.SYMBOLS)
+    L = ctypes.CDLL(pb.lib_path())
+    for s in declared:
+        assert hasattr(L, s), s
+    assert pb.load_library().pb2_version() == 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pb.PB2Error) as e:
+        pb.B200BilinearIntegrator("ket", np.zeros((4, 4)), [np.zeros((4, 4))], K=5, D=10,
+                                  x_off=0, dt_off=4, u_off=6)
+    assert e.value.code == 3
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "piccolo.jl_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f
+
+
+def test_generators_match_oracle_restatement():
+    rng = np.random.default_rng(3)
+    n = 3
+    H = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    H = H + H.conj().T
+    Lop = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    assert np.array_equal(pb.G(H), oiso.G(H))
+    assert np.array_equal(pb.iso(H), oiso.iso(H))
+    assert np.allclose(pb.iso_D(Lop), oiso.iso_D(Lop))
+    assert np.array_equal(pb.density_lift_matrix(n), oiso.density_lift_matrix(n))
+    assert np.array_equal(pb.density_projection_matrix(n), oiso.density_projection_matrix(n))
+    s = S.OpenQuantumSystem(H, [H * 0.5], [1.0], [Lop])
+    G0, Gj = S.compact_generator_parts(s)
+    G0p, Gjp = pb.OpenQuantumSystem(H, [H * 0.5], [1.0], [Lop]).G_parts()
+    assert np.allclose(G0, G0p) and np.allclose(Gj[0], Gjp[0])
+    with pytest.raises(ValueError):
+        pb.QuantumSystem(np.array([[0, 1], [0, 0]]), [])
+
+
+def test_knot_partition():
+    per, rng_ = pb.knot_partition(999, 8)
+    assert per == 125 and rng_[0] == (0, 125) and rng_[-1] == (875, 999)
+    per, rng_ = pb.knot_partition(3, 8)
+    assert per == 1 and rng_[2] == (2, 3) and rng_[3] == (3, 3)
+    assert pb.knot_partition(0, 4)[0] == 0
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+import piccolo_b200 as pb
+from oracle import configs as C, knot as KN
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+p, Z, mu = C.trajectory(2, {K})
+
+class CpuStandIn:                     # test-only injection; the product default is the CUDA handle
+    def __init__(self, K_local, knot0):
+        self.p = KN.make_problem(p.kind, p.G0, p.Gj, K_local)
+    def residual_jacobian(self, Zl):
+        Zl = np.asfortranarray(Zl)
+        return KN.residual(self.p, Zl), KN.jacobian_values(self.p, Zl)
+
+S = pb.ShardedBilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off, dt_off=p.dt_off,
+        u_off=p.u_off, rank=rank, world=world, tensor_device="cpu", make_local=CpuStandIn)
+S.residual_jacobian(Z)
+d, v = S.unpack()
+assert np.array_equal(d, KN.residual(p, Z)), "delta mismatch"
+assert np.array_equal(v, KN.jacobian_values(p, Z)), "jac mismatch"
+dist.barrier()
+if rank == 0: print("SHARD_OK", S.per, S.ranges)
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("K", [10, 4, 2])
+def test_sharded_gather_world2_gloo(tmp_path, K):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, K=K))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(29500 + K), WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [pr.communicate(timeout=240)[0].decode() for pr in procs]
+    assert all(pr.returncode == 0 for pr in procs), outs
+    assert "SHARD_OK" in outs[0]
