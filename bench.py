@@ -188,7 +188,11 @@ def run_ours(args):
             zz += 1e-9 * rng.standard_normal(zz.size)
         Zs.append(torch.from_numpy(zz).to(dev))
         outs.append(torch.empty(chunk * world, dtype=torch.float64, device=dev))
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the kernels, the timing events and (N > 1) the collective
+    # all go on it, so the CUDA events bracket exactly the work they claim to
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
 
     def step(i):
         s = i % nsets

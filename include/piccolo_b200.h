@@ -108,13 +108,16 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
 /* Hessian of sum_k mu_k . delta_k, upper triangle, in pb2_structure_hess order */
 int pb2_hess_lagrangian(pb2_handle* h, const double* Z, const double* mu, double* vals, int space);
 
-/* Device-pointer, asynchronous forms: enqueue on `stream` (a cudaStream_t; NULL = the
- * handle's own stream) and return without synchronizing.  delta / vals / hess may be NULL
- * to skip that output. */
+/* Device-pointer, asynchronous forms: enqueue on `stream` (a cudaStream_t, used exactly as
+ * given: NULL is CUDA's default stream, as everywhere in the runtime API) and return without
+ * synchronizing.  pb2_stream() returns the handle's own non-blocking stream (the one the
+ * host-pointer calls use); pb2_sync() waits for it.  delta / vals may be NULL to skip that
+ * output. */
 int pb2_residual_jacobian_async(pb2_handle* h, const double* dZ, double* ddelta, double* dvals,
                                 void* stream);
 int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu, double* dvals,
                               void* stream);
+void* pb2_stream(const pb2_handle* h);
 int pb2_sync(pb2_handle* h);
 
 /* pinned host memory for callers that want DMA without the staging copy */

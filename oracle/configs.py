@@ -72,7 +72,7 @@ def trajectory(cfg, K=None, noise=1e-3):
     rng = np.random.default_rng(SEED0 + cfg)
     K = p.K
     Z = np.zeros((p.D, K), order="F")
-    dt = duration / (K - 1)
+    dt = duration / max(K - 1, 1)
     Z[p.dt_off, :] = dt
     Z[p.dt_off + 1, :] = dt * np.arange(K)
     bnd = np.asarray(bounds, dtype=float)

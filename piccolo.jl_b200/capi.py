@@ -17,7 +17,7 @@ SYMBOLS = [
     "pb2_dim", "pb2_nnz_jac", "pb2_nnz_hess", "pb2_algorithm", "pb2_structure_jac",
     "pb2_structure_hess", "pb2_residual", "pb2_jacobian", "pb2_residual_jacobian",
     "pb2_hess_lagrangian", "pb2_residual_jacobian_async", "pb2_hess_lagrangian_async",
-    "pb2_sync", "pb2_host_alloc", "pb2_host_free", "pb2_launch_count",
+    "pb2_stream", "pb2_sync", "pb2_host_alloc", "pb2_host_free", "pb2_launch_count",
 ]
 
 
@@ -76,6 +76,8 @@ def load_library():
     L.pb2_residual_jacobian_async.argtypes = [H, vp, vp, vp, vp]
     L.pb2_hess_lagrangian_async.argtypes = [H, vp, vp, vp, vp]
     L.pb2_sync.argtypes = [H]
+    L.pb2_stream.argtypes = [H]
+    L.pb2_stream.restype = ctypes.c_void_p
     L.pb2_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_int64]
     L.pb2_host_free.argtypes = [vp]
     _lib = L

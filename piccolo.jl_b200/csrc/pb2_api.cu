@@ -378,7 +378,7 @@ int pb2_residual_jacobian_async(pb2_handle* h, const double* dZ, double* ddelta,
   if (check(h)) return PB2_EINVAL;
   if (!dZ) return fail(PB2_EINVAL, "pb2_residual_jacobian_async: null Z");
   PB2_CUDA(cudaSetDevice(h->d.device));
-  return launch_resjac(h, dZ, ddelta, dvals, stream ? (cudaStream_t)stream : h->stream);
+  return launch_resjac(h, dZ, ddelta, dvals, (cudaStream_t)stream);
 }
 
 int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu, double* dvals,
@@ -386,8 +386,10 @@ int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu
   if (check(h)) return PB2_EINVAL;
   if (!dZ || !dmu || !dvals) return fail(PB2_EINVAL, "pb2_hess_lagrangian_async: null argument");
   PB2_CUDA(cudaSetDevice(h->d.device));
-  return launch_hess(h, dZ, dmu, dvals, stream ? (cudaStream_t)stream : h->stream);
+  return launch_hess(h, dZ, dmu, dvals, (cudaStream_t)stream);
 }
+
+void* pb2_stream(const pb2_handle* h) { return h ? (void*)h->stream : nullptr; }
 
 int pb2_sync(pb2_handle* h) {
   if (check(h)) return PB2_EINVAL;

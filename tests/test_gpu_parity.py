@@ -165,17 +165,26 @@ def test_device_pointer_api_matches_host_api():
     B = make(p)
     d, v = B.residual_jacobian(Z)
     dZ = torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda()
-    dd = torch.empty(B.dim, dtype=torch.float64, device="cuda")
-    dv = torch.empty(B.nnz_jac, dtype=torch.float64, device="cuda")
-    B.residual_jacobian_device(dZ, dd, dv, torch.cuda.current_stream().cuda_stream)
-    torch.cuda.synchronize()
-    assert np.array_equal(dd.cpu().numpy(), d) and np.array_equal(dv.cpu().numpy(), v)
-    dh = torch.empty(B.nnz_hess, dtype=torch.float64, device="cuda")
+    dd = torch.zeros(B.dim, dtype=torch.float64, device="cuda")
+    dv = torch.zeros(B.nnz_jac, dtype=torch.float64, device="cuda")
+    dh = torch.zeros(B.nnz_hess, dtype=torch.float64, device="cuda")
     dmu = torch.from_numpy(mu).cuda()
-    B.hessian_device(dZ, dmu, dh, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
+    # the kernels must run on the stream that is passed: synchronizing THAT stream only
+    # (not the device) has to be enough to see the results
+    side = torch.cuda.Stream()
+    assert side.cuda_stream != 0
+    B.residual_jacobian_device(dZ, dd, dv, side.cuda_stream)
+    B.hessian_device(dZ, dmu, dh, side.cuda_stream)
+    side.synchronize()
+    assert np.array_equal(dd.cpu().numpy(), d) and np.array_equal(dv.cpu().numpy(), v)
     assert np.array_equal(dh.cpu().numpy(), B.hessian_values(Z, mu))
-    assert B.launch_count >= 4
+    # stream=None is CUDA's default stream
+    dd.zero_()
+    B.residual_jacobian_device(dZ, dd, None, None)
+    torch.cuda.default_stream().synchronize()
+    assert np.array_equal(dd.cpu().numpy(), d)
+    assert B.launch_count >= 5
     B.close()
 
 
