@@ -55,9 +55,10 @@ enum {
 };
 
 enum {
-  PB2_ALG_AUTO = 0,      /* hermitian-eigen path for ket/unitary when available, else generic */
-  PB2_ALG_GENERIC = 1,   /* scaling-and-squaring Taylor jets; any real generator              */
-  PB2_ALG_HERMITIAN = 2  /* complex Hermitian path (ket / unitary only)                      */
+  PB2_ALG_AUTO = 0,     /* tensor-core path when the generator qualifies, else generic          */
+  PB2_ALG_GENERIC = 1,  /* scaling-and-squaring Taylor jets in shared memory; any real generator */
+  PB2_ALG_DMMA = 2      /* FP64 tensor-core Taylor action, one warp per knot: b <= 16, drive
+                           generators with <= 4 nonzeros per row                                */
 };
 
 typedef struct pb2_desc {

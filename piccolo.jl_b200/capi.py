@@ -7,9 +7,9 @@ _SO = os.path.join(_HERE, "libpiccolo_b200.so")
 
 PB2_KET, PB2_UNITARY, PB2_DENSITY = 0, 1, 2
 PB2_HOST, PB2_DEVICE = 0, 1
-PB2_ALG_AUTO, PB2_ALG_GENERIC, PB2_ALG_HERMITIAN = 0, 1, 2
+PB2_ALG_AUTO, PB2_ALG_GENERIC, PB2_ALG_DMMA = 0, 1, 2
 KIND = {"ket": PB2_KET, "unitary": PB2_UNITARY, "density": PB2_DENSITY}
-ALG = {"auto": PB2_ALG_AUTO, "generic": PB2_ALG_GENERIC, "hermitian": PB2_ALG_HERMITIAN}
+ALG = {"auto": PB2_ALG_AUTO, "generic": PB2_ALG_GENERIC, "dmma": PB2_ALG_DMMA}
 
 # every symbol include/piccolo_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [

@@ -17,7 +17,7 @@
 
 #include "../../include/piccolo_b200.h"
 #include "knot_generic.cuh"
-#include "knot_hermitian.cuh"
+#include "knot_dmma.cuh"
 
 namespace {
 
@@ -83,7 +83,9 @@ struct pb2_handle {
   int alg = PB2_ALG_GENERIC;
   cudaStream_t stream = nullptr;
   double *dG0 = nullptr, *dGj = nullptr;
-  pb2::HermitianConsts* dHerm = nullptr;
+  pb2::DmmaPlan plan;          // tensor-core path tables (host copy) and their device mirrors
+  double* dGfrag = nullptr;
+  pb2::EllEntry* dEll = nullptr;
   // staging for host-pointer calls
   double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
   double *hZ = nullptr, *hDelta = nullptr, *hJac = nullptr, *hMu = nullptr, *hHess = nullptr;
@@ -111,9 +113,21 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
   if (h->nk() <= 0) return PB2_OK;
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.delta = ddelta; p.jac = djac;
-  if (h->alg == PB2_ALG_HERMITIAN) {
-    cudaError_t e = pb2::launch_hermitian_resjac(p, h->dHerm, st);
-    if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("hermitian resjac launch: ") + cudaGetErrorString(e));
+  if (h->alg == PB2_ALG_DMMA) {
+    // residual-only calls carry just the state columns; anything with a Jacobian carries the
+    // propagator columns and one jet per drive as well
+    const bool jets = djac != nullptr;
+    pb2::DmmaParams q{};
+    q.b = p.b; q.n_b = p.n_b; q.m = p.m; q.K = p.K; q.D = p.D;
+    q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off; q.nnz_jac = p.nnz_jac;
+    q.ncT = jets ? h->plan.ncT : 0;
+    q.m_jets = jets ? p.m : 0;
+    q.W = h->plan.W; q.iso = h->plan.iso; q.max_sub = 4096;
+    q.Gfrag = h->dGfrag; q.ell = h->dEll; q.Z = dZ; q.delta = ddelta; q.jac = djac;
+    const bool vec = (p.b % (h->plan.iso ? 4 : 2) == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0);
+    cudaError_t e = pb2::dmma_launch(h->plan.NT, jets ? h->plan.tiles_full : h->plan.tiles_res, vec, q,
+                                     (int)h->nk(), pb2::dmma_smem_bytes(h->plan, p.n_b, p.m, jets), st);
+    if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("dmma resjac launch: ") + cudaGetErrorString(e));
   } else {
     const LaunchCfg& c = h->cfg1;
     const int blocks = (int)((h->nk() + c.KPC - 1) / c.KPC);
@@ -128,10 +142,8 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
   if (h->nk() <= 0) return PB2_OK;
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.mu = dmu; p.hess = dhess;
-  if (h->alg == PB2_ALG_HERMITIAN) {
-    cudaError_t e = pb2::launch_hermitian_hess(p, h->dHerm, st);
-    if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("hermitian hess launch: ") + cudaGetErrorString(e));
-  } else {
+  {
+    // the Lagrangian Hessian always runs the jet kernel (second-order jets)
     const LaunchCfg& c = h->cfg2;
     const int blocks = (int)((h->nk() + c.KPC - 1) / c.KPC);
     pb2::knot_generic_kernel<2, kNT><<<blocks, kNT, c.smem, st>>>(p, c.GS, c.KPC, c.gj_in_smem);
@@ -223,7 +235,7 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
   if (!inside(d.x_off, n_x) || !inside(d.dt_off, 1) || !inside(d.u_off, d.m))
     return fail(PB2_EINVAL, "pb2_create: component offsets outside the knot column");
   if (!d.G0 || (d.m > 0 && !d.Gj)) return fail(PB2_EINVAL, "pb2_create: null generator");
-  if (d.algorithm < PB2_ALG_AUTO || d.algorithm > PB2_ALG_HERMITIAN)
+  if (d.algorithm < PB2_ALG_AUTO || d.algorithm > PB2_ALG_DMMA)
     return fail(PB2_EINVAL, "pb2_create: bad algorithm");
 
   int ndev = 0;
@@ -245,19 +257,22 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
   h->d.Gj = h->Gj.data();
 
   // algorithm selection (decided once, at construction -- never a runtime fallback)
-  const bool herm_ok = (d.kind != PB2_DENSITY) &&
-                       pb2::hermitian_supported(d.b, d.n_b, d.m, h->G0.data(), h->Gj.data());
-  if (d.algorithm == PB2_ALG_HERMITIAN && !herm_ok) {
+  // the tensor-core path covers generators up to 16 x 16 with sparse drive terms; ket / unitary
+  // generators additionally use the half (real-isomorphism) layout of the propagator
+  if (d.algorithm != PB2_ALG_GENERIC)
+    h->plan = pb2::dmma_plan(d.b, d.n_b, d.m, d.kind != PB2_DENSITY, h->G0.data(), h->Gj.data());
+  if (d.algorithm == PB2_ALG_DMMA && !h->plan.ok) {
     delete h;
-    return fail(PB2_EINVAL, "pb2_create: hermitian path unsupported for this generator/size");
+    return fail(PB2_EINVAL, "pb2_create: tensor-core path unsupported for this generator "
+                            "(needs b <= 16, <= 4 nonzeros per drive-generator row, <= 8 column tiles)");
   }
-  h->alg = (d.algorithm == PB2_ALG_GENERIC || !herm_ok) ? PB2_ALG_GENERIC : PB2_ALG_HERMITIAN;
+  h->alg = h->plan.ok ? PB2_ALG_DMMA : PB2_ALG_GENERIC;
 
-  if (h->alg == PB2_ALG_GENERIC) {
-    if (!plan_generic(1, d.b, d.n_b, d.m, h->cfg1) || !plan_generic(2, d.b, d.n_b, d.m, h->cfg2)) {
-      delete h;
-      return fail(PB2_EINVAL, "pb2_create: generator too large for the shared-memory kernels");
-    }
+  // the jet kernels: residual/Jacobian when the tensor-core path is off, the Hessian always
+  const bool need1 = h->alg == PB2_ALG_GENERIC;
+  if ((need1 && !plan_generic(1, d.b, d.n_b, d.m, h->cfg1)) || !plan_generic(2, d.b, d.n_b, d.m, h->cfg2)) {
+    delete h;
+    return fail(PB2_EINVAL, "pb2_create: generator too large for the shared-memory kernels");
   }
 
   auto cleanup_fail = [&](int code, const std::string& msg) {
@@ -283,15 +298,17 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
   for (int q = 1; q <= pb2::kMaxDeg; ++q) theta[q] = theta_bound(q);
   PB2_CUDA_H(cudaMemcpyToSymbol(pb2::c_theta, theta, sizeof(theta)));
 
-  if (h->alg == PB2_ALG_GENERIC) {
+  if (h->alg == PB2_ALG_GENERIC)
     PB2_CUDA_H(cudaFuncSetAttribute(pb2::knot_generic_kernel<1, kNT>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cfg1.smem));
-    PB2_CUDA_H(cudaFuncSetAttribute(pb2::knot_generic_kernel<2, kNT>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cfg2.smem));
-  } else {
-    cudaError_t e = pb2::hermitian_setup(d.b, d.n_b, d.m, h->G0.data(), h->Gj.data(), &h->dHerm);
-    if (e != cudaSuccess)
-      return cleanup_fail(PB2_ECUDA, std::string("hermitian_setup: ") + cudaGetErrorString(e));
+  PB2_CUDA_H(cudaFuncSetAttribute(pb2::knot_generic_kernel<2, kNT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cfg2.smem));
+  if (h->alg == PB2_ALG_DMMA) {
+    const size_t ng = h->plan.gfrag.size() * sizeof(double), ne = h->plan.ell.size() * sizeof(pb2::EllEntry);
+    PB2_CUDA_H(cudaMalloc(&h->dGfrag, ng));
+    PB2_CUDA_H(cudaMalloc(&h->dEll, ne));
+    PB2_CUDA_H(cudaMemcpy(h->dGfrag, h->plan.gfrag.data(), ng, cudaMemcpyHostToDevice));
+    PB2_CUDA_H(cudaMemcpy(h->dEll, h->plan.ell.data(), ne, cudaMemcpyHostToDevice));
   }
 #undef PB2_CUDA_H
   *out = h;
@@ -304,7 +321,8 @@ void pb2_destroy(pb2_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (double* p : {h->dG0, h->dGj, h->dZ, h->dDelta, h->dJac, h->dMu, h->dHess})
     if (p) cudaFree(p);
-  if (h->dHerm) cudaFree(h->dHerm);
+  if (h->dGfrag) cudaFree(h->dGfrag);
+  if (h->dEll) cudaFree(h->dEll);
   for (double* p : {h->hZ, h->hDelta, h->hJac, h->hMu, h->hHess})
     if (p) cudaFreeHost(p);
   if (h->stream) cudaStreamDestroy(h->stream);

@@ -146,7 +146,7 @@ class B200BilinearIntegrator:
         self.dim = int(self._lib.pb2_dim(h))
         self.nnz_jac = int(self._lib.pb2_nnz_jac(h))
         self.nnz_hess = int(self._lib.pb2_nnz_hess(h))
-        self.algorithm = {1: "generic", 2: "hermitian"}[self._lib.pb2_algorithm(h)]
+        self.algorithm = {1: "generic", 2: "dmma"}[self._lib.pb2_algorithm(h)]
 
     def close(self):
         if getattr(self, "_h", None):

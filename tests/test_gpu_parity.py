@@ -192,10 +192,118 @@ def test_error_behaviour():
     p, Z, mu = C.trajectory(1, 5)
     with pytest.raises(pb.PB2Error):
         pb.B200BilinearIntegrator("unitary", p.G0, list(p.Gj), K=5, D=3, x_off=0, dt_off=8, u_off=10)
+    big = np.zeros((18, 18))   # the tensor-core path refuses what it cannot do (b > 16)
     with pytest.raises(pb.PB2Error):
-        pb.B200BilinearIntegrator("density", p.G0, list(p.Gj), K=5, D=p.D, x_off=0, dt_off=8,
-                                  u_off=10, algorithm="hermitian")
+        pb.B200BilinearIntegrator("density", big, [big], K=5, D=18 + 5, x_off=0, dt_off=18,
+                                  u_off=20, algorithm="dmma")
     B = make(p)
     with pytest.raises(ValueError):
         B.residual_jacobian(Z[:, :3])
     B.close()
+
+
+def _random_problem(kind, b, m, K, seed):
+    """Random generators whose drive terms stay within the tensor-core path's ELL width."""
+    rng = np.random.default_rng(seed)
+    if kind == "density":
+        G0 = rng.standard_normal((b, b)) * (rng.random((b, b)) < 0.6)
+        Gj = []
+        for _ in range(m):
+            g = np.zeros((b, b))
+            for r in range(b):
+                cols = rng.choice(b, size=min(b, int(rng.integers(0, 4))), replace=False)
+                g[r, cols] = rng.standard_normal(cols.size)
+            Gj.append(g)
+    else:
+        d = b // 2
+
+        def iso_gen(H):
+            return np.block([[H.imag, H.real], [-H.real, H.imag]])
+        H0 = rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))
+        G0 = iso_gen(H0 + H0.conj().T)
+        Gj = []
+        for _ in range(m):
+            H = np.zeros((d, d), dtype=complex)
+            perm = rng.permutation(d)
+            for a in range(0, d - 1, 2):          # random pairing: <= 1 complex entry per row
+                i, j = perm[a], perm[a + 1]
+                H[i, j] = rng.standard_normal() + 1j * rng.standard_normal()
+                H[j, i] = np.conj(H[i, j])
+            H[perm[-1], perm[-1]] += rng.standard_normal()
+            Gj.append(iso_gen(H))
+    p = KN.make_problem(kind, G0, Gj, K)
+    Z = np.asfortranarray(rng.standard_normal((p.D, K)) * 0.3)
+    Z[p.dt_off, :] = 0.05 + 0.1 * rng.random(K)
+    return p, Z, rng.standard_normal(p.dim)
+
+
+@pytest.mark.parametrize("kind,b,m", [("density", 9, 2), ("density", 4, 1), ("density", 16, 3),
+                                      ("density", 5, 0), ("ket", 6, 2), ("ket", 16, 3), ("ket", 2, 1),
+                                      ("unitary", 6, 2), ("unitary", 12, 1), ("unitary", 16, 6)])
+def test_tensor_core_path_shapes(kind, b, m):
+    """Odd / padded generator sizes, m = 0, mixed tiles (propagator, state and jet columns sharing
+    one 8-column tile), the widest supported problem (8 tiles)."""
+    p, Z, mu = _random_problem(kind, b, m, 9, seed=100 * b + m)
+    B = make(p, "dmma")
+    assert B.algorithm == "dmma"
+    d, v = B.residual_jacobian(Z)
+    assert np.abs(d - KN.residual(p, Z)).max() < 1e-11
+    assert np.abs(v - KN.jacobian_values(p, Z)).max() < 1e-10
+    d2 = np.empty(B.dim)
+    B.evaluate_(d2, Z)                       # residual-only launch carries no jets
+    assert np.abs(d2 - d).max() < 1e-13
+    assert np.array_equal(v, B.jacobian_values(Z))
+    B.close()
+
+
+def test_tensor_core_path_substeps_and_limits():
+    """||dt G|| from tiny to ~60: the number of Taylor sub-steps is data dependent per knot."""
+    p, Z, mu = C.trajectory(2, 12)
+    Z[p.dt_off, :] = np.geomspace(1e-6, 6.0, p.K)
+    B = make(p, "dmma")
+    d, v = B.residual_jacobian(Z)
+    assert np.abs(d - KN.residual(p, Z)).max() < 1e-10
+    assert np.abs(v - KN.jacobian_values(p, Z)).max() < 2e-9
+    # NaN / inf inputs poison only their own knot
+    Z2 = Z.copy(order="F")
+    Z2[p.u_off, 3] = np.nan
+    Z2[p.dt_off, 5] = np.inf
+    d2, v2 = B.residual_jacobian(Z2)
+    D2 = d2.reshape(p.K - 1, p.n_x)
+    assert np.isnan(D2[3]).all() and np.isnan(D2[5]).all()
+    ok = [k for k in range(p.K - 1) if k not in (3, 5)]
+    assert np.array_equal(D2[ok], d.reshape(p.K - 1, p.n_x)[ok])
+    B.close()
+
+
+def test_tensor_core_path_unaligned_outputs():
+    """Device pointers that are only 8-byte aligned take the scalar-store variant."""
+    import torch
+    p, Z, mu = C.trajectory(3, 6)
+    B = make(p, "dmma")
+    d, v = B.residual_jacobian(Z)
+    dZ = torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda()
+    buf = torch.zeros(B.dim + B.nnz_jac + 3, dtype=torch.float64, device="cuda")
+    dd, dv = buf[1:1 + B.dim], buf[2 + B.dim:2 + B.dim + B.nnz_jac]
+    assert dd.data_ptr() % 16 == 8
+    B.residual_jacobian_device(dZ, dd, dv, None)
+    torch.cuda.synchronize()
+    assert np.array_equal(dd.cpu().numpy(), d) and np.array_equal(dv.cpu().numpy(), v)
+    assert buf[0].item() == 0.0 and buf[1 + B.dim].item() == 0.0 and buf[-1].item() == 0.0
+    B.close()
+
+
+def test_auto_falls_back_to_jets_at_construction():
+    """A dense drive generator is outside the tensor-core path: auto picks the jet kernels when the
+    handle is built (never a runtime fallback), dmma refuses."""
+    rng = np.random.default_rng(5)
+    b = 8
+    p = KN.make_problem("density", rng.standard_normal((b, b)), [rng.standard_normal((b, b))], 6)
+    Z = np.asfortranarray(0.2 * rng.standard_normal((p.D, 6)))
+    B = make(p, "auto")
+    assert B.algorithm == "generic"
+    d, v = B.residual_jacobian(Z)
+    assert np.abs(d - KN.residual(p, Z)).max() < 1e-11
+    B.close()
+    with pytest.raises(pb.PB2Error):
+        make(p, "dmma")
