@@ -3,7 +3,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libpiccolo_b200.so")
+# PB2_LIB selects an alternative build of the same library (e.g. the -DPB2_TRACE debug build)
+_SO = os.path.join(_HERE, os.environ.get("PB2_LIB", "libpiccolo_b200.so"))
 
 PB2_KET, PB2_UNITARY, PB2_DENSITY = 0, 1, 2
 PB2_HOST, PB2_DEVICE = 0, 1

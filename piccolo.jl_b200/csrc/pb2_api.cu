@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -85,6 +86,10 @@ struct pb2_handle {
   double *dG0 = nullptr, *dGj = nullptr;
   pb2::DmmaPlan plan;          // tensor-core path tables (host copy) and their device mirrors
   double* dGfrag = nullptr;
+  double* dNorms = nullptr;
+  long long* dTrace = nullptr;
+  long long* dTrace2 = nullptr;
+  int n_sm = 148, gpc_default = 3, gpc_override = 0;
   pb2::EllEntry* dEll = nullptr;
   // staging for host-pointer calls
   double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
@@ -117,16 +122,31 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     // residual-only calls carry just the state columns; anything with a Jacobian carries the
     // propagator columns and one jet per drive as well
     const bool jets = djac != nullptr;
+    const pb2::DmmaPlan& pl = h->plan;
     pb2::DmmaParams q{};
-    q.b = p.b; q.n_b = p.n_b; q.m = p.m; q.K = p.K; q.D = p.D;
+    q.b = p.b; q.n_b = p.n_b; q.m = p.m; q.D = p.D;
     q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off; q.nnz_jac = p.nnz_jac;
-    q.ncT = jets ? h->plan.ncT : 0;
+    q.ncT = jets ? pl.ncT : 0;
     q.m_jets = jets ? p.m : 0;
-    q.W = h->plan.W; q.iso = h->plan.iso; q.max_sub = 4096;
-    q.Gfrag = h->dGfrag; q.ell = h->dEll; q.Z = dZ; q.delta = ddelta; q.jac = djac;
-    const bool vec = (p.b % (h->plan.iso ? 4 : 2) == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0);
-    cudaError_t e = pb2::dmma_launch(h->plan.NT, jets ? h->plan.tiles_full : h->plan.tiles_res, vec, q,
-                                     (int)h->nk(), pb2::dmma_smem_bytes(h->plan, p.n_b, p.m, jets), st);
+    q.iso = pl.iso; q.max_sub = 4096;
+    q.tiles = jets ? pl.tiles_full : pl.tiles_res;
+    q.nk = (int)h->nk();
+    q.zlen = p.D + p.x_off + p.b * p.n_b;
+    q.Gfrag = h->dGfrag; q.ell = h->dEll; q.norms = h->dNorms;
+    q.Z = dZ; q.delta = ddelta; q.jac = djac; q.trace = h->dTrace;
+    const int bb = p.b * p.b, n_x = p.b * p.n_b;
+    q.bulk_in = (p.D % 2 == 0) && (q.zlen % 2 == 0) && ((uintptr_t)dZ % 16 == 0);
+    q.bulk_out = (bb % 2 == 0) && (n_x % 2 == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0);
+    // persistent grid: one CTA per SM, gpc knot groups per CTA (bounded by threads, barriers, smem)
+    int maxg = std::min(pb2::kDmmaMaxGroups, pb2::kDmmaMaxThreads / (32 * q.tiles));
+    while (maxg > 1 && pb2::dmma_layout(q, pl.NT, maxg) > kSmemLimit) --maxg;
+    const int per_sm = (q.nk + h->n_sm - 1) / h->n_sm;
+    q.gpc = std::max(1, std::min(maxg, h->gpc_override > 0 ? h->gpc_override : std::min(per_sm, h->gpc_default)));
+    const int blocks = std::min(h->n_sm, (q.nk + q.gpc - 1) / q.gpc);
+    const size_t smem = pb2::dmma_layout(q, pl.NT, q.gpc);
+    if (smem > kSmemLimit) return fail(PB2_EINVAL, "dmma resjac: knot column too large for the shared-memory staging");
+    pb2::dmma_kernel(pl.NT, pl.W)<<<blocks, 32 * q.tiles * q.gpc, smem, st>>>(q);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("dmma resjac launch: ") + cudaGetErrorString(e));
   } else {
     const LaunchCfg& c = h->cfg1;
@@ -305,10 +325,32 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cfg2.smem));
   if (h->alg == PB2_ALG_DMMA) {
     const size_t ng = h->plan.gfrag.size() * sizeof(double), ne = h->plan.ell.size() * sizeof(pb2::EllEntry);
+    const size_t nn = h->plan.norms.size() * sizeof(double);
     PB2_CUDA_H(cudaMalloc(&h->dGfrag, ng));
     PB2_CUDA_H(cudaMalloc(&h->dEll, ne));
+    PB2_CUDA_H(cudaMalloc(&h->dNorms, nn));
     PB2_CUDA_H(cudaMemcpy(h->dGfrag, h->plan.gfrag.data(), ng, cudaMemcpyHostToDevice));
     PB2_CUDA_H(cudaMemcpy(h->dEll, h->plan.ell.data(), ne, cudaMemcpyHostToDevice));
+    PB2_CUDA_H(cudaMemcpy(h->dNorms, h->plan.norms.data(), nn, cudaMemcpyHostToDevice));
+    double invfact[pb2::kMaxDeg + 1];
+    invfact[0] = 1.0;
+    for (int q = 1; q <= pb2::kMaxDeg; ++q) invfact[q] = invfact[q - 1] / (double)q;
+    PB2_CUDA_H(cudaMemcpyToSymbol(pb2::c_invfact, invfact, sizeof(invfact)));
+    PB2_CUDA_H(cudaFuncSetAttribute(pb2::dmma_kernel(h->plan.NT, h->plan.W),
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    PB2_CUDA_H(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, d.device));
+    if (const char* env = std::getenv("PB2_GPC")) h->gpc_override = std::atoi(env);
+#ifdef PB2_TRACE
+    PB2_CUDA_H(cudaMalloc(&h->dTrace, 8 * 16 * 8 * sizeof(long long)));
+    PB2_CUDA_H(cudaMemset(h->dTrace, 0, 8 * 16 * 8 * sizeof(long long)));
+    {
+      long long* t2 = nullptr;
+      PB2_CUDA_H(cudaMalloc(&t2, 16 * 20 * 4 * sizeof(long long)));
+      PB2_CUDA_H(cudaMemset(t2, 0, 16 * 20 * 4 * sizeof(long long)));
+      PB2_CUDA_H(cudaMemcpyToSymbol(pb2::g_trace2, &t2, sizeof(t2)));
+      h->dTrace2 = t2;
+    }
+#endif
   }
 #undef PB2_CUDA_H
   *out = h;
@@ -323,6 +365,8 @@ void pb2_destroy(pb2_handle* h) {
     if (p) cudaFree(p);
   if (h->dGfrag) cudaFree(h->dGfrag);
   if (h->dEll) cudaFree(h->dEll);
+  if (h->dNorms) cudaFree(h->dNorms);
+  if (h->dTrace) cudaFree(h->dTrace);
   for (double* p : {h->hZ, h->hDelta, h->hJac, h->hMu, h->hHess})
     if (p) cudaFreeHost(p);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -335,6 +379,18 @@ int64_t pb2_nnz_jac(const pb2_handle* h) { return h ? (int64_t)h->nnz_jac_knot()
 int64_t pb2_nnz_hess(const pb2_handle* h) { return h ? (int64_t)h->nnz_hess_knot() * h->nk() : -1; }
 int32_t pb2_algorithm(const pb2_handle* h) { return h ? h->alg : -1; }
 int64_t pb2_launch_count(const pb2_handle* h) { return h ? h->launches : -1; }
+#ifdef PB2_TRACE
+extern "C" int pb2_debug_trace(pb2_handle* h, long long* out) {   // 8 knots x 16 warps x 8 stamps
+  if (!h || !h->dTrace) return PB2_EINVAL;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(out, h->dTrace, 8 * 16 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : PB2_ECUDA;
+}
+extern "C" int pb2_debug_trace2(pb2_handle* h, long long* out) {   // 16 warps x 20 steps x 4 stamps (last knot)
+  if (!h || !h->dTrace2) return PB2_EINVAL;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(out, h->dTrace2, 16 * 20 * 4 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : PB2_ECUDA;
+}
+#endif
 
 int pb2_structure_jac(const pb2_handle* h, int64_t* rows, int64_t* cols) {
   if (check(h)) return PB2_EINVAL;

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Debug: per-phase clock64 stamps of block 0 of the tensor-core knot kernel (needs a library built
+with -DPB2_TRACE:  make -C piccolo.jl_b200 TRACE=1 libpiccolo_b200_trace.so)."""
+import ctypes, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("PB2_LIB", "libpiccolo_b200_trace.so")
+import piccolo_b200 as pb
+from oracle import configs as C
+
+cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+p, Z, _ = C.trajectory(cfg)
+B = pb.B200BilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off, dt_off=p.dt_off, u_off=p.u_off)
+for _ in range(3):
+    B.residual_jacobian(Z)
+out = np.zeros(8 * 16 * 8, dtype=np.int64)
+lib = pb.load_library()
+lib.pb2_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+assert lib.pb2_debug_trace(B._h, out.ctypes.data) == 0
+T = out.reshape(8, 16, 8)
+t0 = T[T > 0].min()
+names = ["start", "slab", "prebar", "postbar", "loaded", "horner", "staged", "postbar2"]
+for it in range(8):
+    for w in range(16):
+        if T[it, w].max() > 0:
+            print(f"knot {it} warp {w:2d}: " + " ".join(f"{n}={int(v - t0):6d}" for n, v in zip(names, T[it, w])))
+
+out2 = np.zeros(16 * 20 * 4, dtype=np.int64)
+lib.pb2_debug_trace2.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+assert lib.pb2_debug_trace2(B._h, out2.ctypes.data) == 0
+T2 = out2.reshape(16, 20, 4)
+t0 = T2[T2 > 0].min()
+print("per-step stamps of the last knot of block 0 (entry, before barrier, end):")
+for w in range(16):
+    for st in range(19, -1, -1):
+        if T2[w, st].max() > 0:
+            print(f"warp {w:2d} kq {st:2d}: " + " ".join(f"{int(v - t0) if v else -1:6d}" for v in T2[w, st, :3]))
