@@ -1,0 +1,462 @@
+// Warp-specialised tensor-core knot kernel for the 3-qubit unitary shape (generator 16 x 16 with
+// real-isomorphism structure, 8 state columns: BASELINE configs C3 / C5), residual + Jacobian.
+//
+// Same mathematics as knot_dmma.cuh (truncated-Taylor action of exp(dt G(u)) on the stacked
+// columns [I | X | jet_1 .. jet_m] by DMMA.8x8x4 with register-resident transposed tiles; the
+// reference path it replaces is DirectTrajOpt's BilinearIntegrator as built at
+// /root/reference/src/control/integrators.jl:35-51), specialised so that every shared-memory
+// offset is an immediate, and organised around what the first profiles showed: one knot is far
+// too little work to hide its own latencies, and the FP64 tensor pipe (one DMMA per 16 cycles per
+// SM sub-partition) idles whenever all warps of a knot wait on the same barrier.
+//
+//   * a knot GROUP = 1 producer warp + 1 warp for the tiles (E, X) + one warp per PAIR of drive
+//     jets; up to 4 groups per persistent CTA work on 4 different knots, so while one group sits
+//     in its exchange barrier or epilogue the others keep the pipe busy.  Roles are rotated by
+//     group so that every sub-partition gets the same number of DMMA-issuing warps.
+//   * the producer warp runs ahead of its group: it receives the (z_k, x_{k+1}) slab by TMA
+//     (cp.async.bulk + mbarrier, 3-deep ring), builds G(u_k) in B-fragment order, picks the Taylor
+//     degree and writes the coefficients a_k = dt^k / k!  -- all for knot i+1 while the compute
+//     warps are inside knot i -- and hands it over through an mbarrier.  After the compute warps
+//     have staged their results it replicates the propagator block (the Jacobian's d/dx_k block
+//     is I (x) E: n_b = 8 copies) inside shared memory and issues ONE bulk store of the knot's
+//     whole COO row segment (22.5 KB) plus one for delta.
+//   * compute warps: per Horner step 16 DMMAs from registers, one named barrier for the X
+//     exchange, then the additive terms (a_k B, sparse G_j S) -- nothing else.
+#pragma once
+#include "knot_dmma.cuh"
+
+namespace pb2 {
+
+struct U8Params {
+  int m, D, x_off, dt_off, u_off, nnz_jac, max_sub, gpc, nk, zlen;
+  int gw;                // warps per group: producer + (E,X) + ceil(m/2) jet warps
+  // shared-memory layout in doubles (u8_layout)
+  int o_norm, o_grp, grp_stride, zpad, o_prep, o_y, o_stage, o_mbar;
+  const double* Gfrag;   // (m+1) * 256 doubles, B-fragment order
+  const EllEntry* ell;   // (m+1) * 16 * W   (drive m = all-zero dummy)
+  const double* norms;   // m+1
+  const double* Z;
+  double* delta;         // may be null
+  double* jac;
+};
+
+constexpr int kU8Prep = 280;        // doubles per prepared knot: G(u) frags 256 | a_k 20 | M, n_sub | pad
+constexpr int kU8MaxGroups = 4;
+constexpr int kU8MaxThreads = 512;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void lds_v2u32(uint32_t addr, int& a, int& b) {
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(addr) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double2 v) {
+  asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(addr), "n"(OFF), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// byte offset of element i (row 8 (i>>1) + 2q + (i&1)) relative to the lane's (column, 2q) address
+#define U8_OFF(i) (((i) >> 1) * 64 + ((i) & 1) * 8)
+
+// t <- G t for one 8-column tile (8 DMMAs, two independent accumulator chains)
+__device__ __forceinline__ void u8_mma(double (&d)[2][2], const double (&t)[4], const double (&A)[4][2]) {
+  dmma884z(d[0], t[0], A[0][0]);
+  dmma884z(d[1], t[0], A[0][1]);
+#pragma unroll
+  for (int kt = 1; kt < 4; ++kt) {
+    dmma884(d[0], t[kt], A[kt][0]);
+    dmma884(d[1], t[kt], A[kt][1]);
+  }
+}
+
+// ---- one Horner step of the (E, X) warp.  FIRST: first sub-step (B = unit columns for E) ------
+template <int PAR, bool FIRST>
+__device__ __forceinline__ void u8_step_ex(double (&tE)[4], double (&tX)[4], const double (&bE)[4],
+                                           const double (&bX)[4], const double (&A)[4][2], int iE, uint32_t ypub,
+                                           uint32_t ck_addr, int xbar, int nx) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) sts_f64<PAR * 1024>(ypub + i * 256, tX[i]);
+  const double ck = lds_f64<0>(ck_addr);
+  double dE[2][2], dX[2][2];
+  u8_mma(dX, tX, A);
+  u8_mma(dE, tE, A);
+  bar_sync(xbar, nx);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    tX[i] = fma(ck, bX[i], dX[i >> 1][i & 1]);
+    if (FIRST) tE[i] = (i == iE) ? dE[i >> 1][i & 1] + ck : dE[i >> 1][i & 1];
+    else tE[i] = fma(ck, bE[i], dE[i >> 1][i & 1]);
+  }
+}
+
+// ---- one Horner step of a jet warp (two jet tiles).  FIRST: B_j = 0; NOMMA: the iterate is zero --
+template <int W, int PAR, bool FIRST, bool NOMMA>
+__device__ __forceinline__ void u8_step_jets(double (&t)[2][4], const double (&bJ)[2][4], const double (&A)[4][2],
+                                             const double (&ev)[2][4][W], const uint32_t (&yad)[2][4][W],
+                                             uint32_t ck_addr, bool two, int xbar, int nx) {
+  double d[2][2][2];
+  if (NOMMA) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a) d[a][0][0] = d[a][0][1] = d[a][1][0] = d[a][1][1] = 0.0;
+  } else {
+    u8_mma(d[0], t[0], A);
+    if (two) u8_mma(d[1], t[1], A);
+  }
+  double ck = 0.0;
+  if (!FIRST) ck = lds_f64<0>(ck_addr);
+  bar_sync(xbar, nx);
+  double y[2][4][W];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int ww = 0; ww < W; ++ww) y[a][i][ww] = lds_f64<PAR * 1024>(yad[a][i][ww]);
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double v = d[a][i >> 1][i & 1];
+      if (!FIRST) v = fma(ck, bJ[a][i], v);
+#pragma unroll
+      for (int ww = 0; ww < W; ++ww) v = fma(ev[a][i][ww], y[a][i][ww], v);
+      t[a][i] = v;
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_constant__ U8Params p) {
+  extern __shared__ __align__(16) double u8_smem[];
+  const int lane = threadIdx.x & 31, wcta = threadIdx.x >> 5;
+  const int gw = p.gw, group = wcta / gw, wg = wcta - group * gw;
+  const int role = (wg + group) % gw;   // 0 producer, 1 (E, X) tiles, 2 + jw: jets 2 jw, 2 jw + 1
+  const int g = lane >> 2, q = lane & 3;
+  const int m = p.m, ncw = gw - 1, nx = 32 * ncw, xbar = 1 + group;
+
+  const uint32_t a_cG = smem_u32(u8_smem);
+  const uint32_t a_grp = a_cG + 8u * (uint32_t)(p.o_grp + group * p.grp_stride);
+  const uint32_t a_prep = a_grp + 8u * p.o_prep, a_y = a_grp + 8u * p.o_y, a_stage = a_grp + 8u * p.o_stage;
+  const uint32_t a_mbar = a_grp + 8u * p.o_mbar;
+  const uint32_t mb_zfull = a_mbar, mb_ready = a_mbar + 24, mb_staged = a_mbar + 40, mb_free = a_mbar + 48;
+  const uint32_t o_J = 8u * 2048u, o_D = 8u * (2048u + (uint32_t)(m + 2) * 128u);   // inside the stage
+
+  // ---- once per CTA ------------------------------------------------------------------------------
+  for (int e = threadIdx.x; e < (m + 1) * 256; e += blockDim.x) u8_smem[e] = p.Gfrag[e];
+  for (int e = threadIdx.x; e <= m; e += blockDim.x) u8_smem[p.o_norm + e] = p.norms[e];
+  {
+    double* ones = u8_smem + p.o_grp + group * p.grp_stride + p.o_stage + 2048 + (m + 1) * 128;
+    for (int e = wg * 32 + lane; e < 128; e += 32 * gw) ones[e] = 1.0;
+  }
+  if (wg == 0 && lane == 0) {
+    for (int i = 0; i < 3; ++i) mbar_init(mb_zfull + 8 * i, 1);
+    mbar_init(mb_ready, 1);
+    mbar_init(mb_ready + 8, 1);
+    mbar_init(mb_staged, ncw);
+    mbar_init(mb_free, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int TG = gridDim.x * p.gpc, gg = group * gridDim.x + blockIdx.x;
+  const int n_my = gg < p.nk ? (p.nk - gg + TG - 1) / TG : 0;
+  const uint32_t zbytes = (uint32_t)p.zlen * 8u;
+
+  if (role == 0) {
+    // =============================== producer warp ===============================================
+    if (lane == 0) {
+      for (int i = 0; i < 2 && i < n_my; ++i) {
+        mbar_expect_tx(mb_zfull + 8 * i, zbytes);
+        bulk_g2s(a_grp + 8u * (uint32_t)(i * p.zpad), p.Z + (size_t)(gg + i * TG) * p.D, zbytes, mb_zfull + 8 * i);
+      }
+      mbar_arrive(mb_free);   // the stage starts free
+    }
+    const double th_l = c_theta[lane <= kMaxDeg ? lane : kMaxDeg];
+    const double if_l = c_invfact[lane <= kMaxDeg ? lane : kMaxDeg];
+    const double th_max = c_theta[kMaxDeg];
+    int s3 = 0;
+    for (int i = 0; i <= n_my; ++i) {
+      if (i < n_my) {
+        // ---- prepare knot i: G(u), Taylor degree, coefficients ------------------------------------
+        const uint32_t a_z = a_grp + 8u * (uint32_t)(s3 * p.zpad);
+        const uint32_t a_p = a_prep + 8u * (uint32_t)((i & 1) * kU8Prep);
+        mbar_wait(mb_zfull + 8 * s3, (uint32_t)((i / 3) & 1));
+        double acc[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) acc[s] = lds_f64<0>(a_cG + 8u * (uint32_t)(s * 32 + lane));
+        double dt = lds_f64<0>(a_z + 8u * p.dt_off);
+        double nrm = lds_f64<0>(a_cG + 8u * p.o_norm);
+        for (int j = 0; j < m; ++j) {
+          const double uj = lds_f64<0>(a_z + 8u * (uint32_t)(p.u_off + j));
+          nrm = fma(fabs(uj), lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_norm + 1 + j)), nrm);
+          const uint32_t a_gj = a_cG + 8u * (uint32_t)((1 + j) * 256 + lane);
+#pragma unroll
+          for (int s = 0; s < 8; ++s) acc[s] = fma(uj, lds_f64<0>(a_gj + 256u * s), acc[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < 8; ++s) sts_f64<0>(a_p + 8u * (uint32_t)(s * 32 + lane), acc[s]);
+        nrm *= fabs(dt);
+        int n_sub = 1;
+        double per = nrm;
+        if (nrm > th_max) {
+          const double ns = ceil(nrm / th_max);
+          if (ns <= (double)p.max_sub) {
+            n_sub = (int)ns;
+            dt = dt / ns;
+            per = nrm / ns;
+          } else {
+            dt = __longlong_as_double(0x7ff8000000000000LL);  // norm beyond the supported range: NaN out
+          }
+        }
+        // M = 1 + #{ l in 1..kMaxDeg-1 : theta_l < per }   (theta increasing; NaN -> M = 1)
+        const unsigned below = __ballot_sync(0xffffffffu, lane >= 1 && lane < kMaxDeg && th_l < per);
+        const int M = 1 + __popc(below);
+        double pw = 1.0, sq = dt;   // dt^lane by binary powering
+#pragma unroll
+        for (int bit = 0; bit < 5; ++bit) {
+          if ((lane >> bit) & 1) pw *= sq;
+          sq *= sq;
+        }
+        if (lane <= kMaxDeg) sts_f64<0>(a_p + 8u * 256u + 8u * lane, lane <= M ? if_l * pw : 0.0);
+        if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_p + 8u * 276u), "r"(M), "r"(n_sub) : "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mb_ready + 8 * (i & 1));
+      }
+      if (i >= 1) {
+        // ---- finish knot i-1: replicate the propagator block, one bulk store per output --------
+        const int kprev = gg + (i - 1) * TG;
+        mbar_wait(mb_staged, (uint32_t)((i - 1) & 1));
+        double2 v[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) v[jj] = lds_f64x2<0>(a_stage + 16u * (uint32_t)(lane + 32 * jj));
+#pragma unroll
+        for (int c = 1; c < 8; ++c)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) sts_f64x2<0>(a_stage + 2048u * c + 16u * (uint32_t)(lane + 32 * jj), v[jj]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(p.jac + (size_t)kprev * p.nnz_jac, a_stage, (uint32_t)p.nnz_jac * 8u);
+          if (p.delta) bulk_s2g(p.delta + (size_t)kprev * 128, a_stage + o_D, 1024u);
+          bulk_commit();
+        }
+      }
+      if (lane == 0) {
+        // slab (i+2)%3 held knot i-1, which is finished
+        if (i + 2 < n_my) {
+          const int s = s3 == 0 ? 2 : s3 - 1;   // (i + 2) % 3
+          mbar_expect_tx(mb_zfull + 8 * s, zbytes);
+          bulk_g2s(a_grp + 8u * (uint32_t)(s * p.zpad), p.Z + (size_t)(gg + (i + 2) * TG) * p.D, zbytes,
+                   mb_zfull + 8 * s);
+        }
+        if (i >= 1) {
+          bulk_wait_read0();        // the stage has been read: the compute warps may refill it
+          mbar_arrive(mb_free);
+        }
+      }
+      __syncwarp();
+      s3 = s3 == 2 ? 0 : s3 + 1;
+    }
+    if (lane == 0) bulk_wait0();
+    return;
+  }
+
+  // ================================= compute warps ==================================================
+  const uint32_t lane_col = 8u * (uint32_t)(g * 16 + 2 * q);   // (column g, row 2q) inside a 16 x 8 block
+  if (role == 1) {
+    // ---- tiles E (columns 0..7 of the propagator) and X (the 8 state columns) -------------------
+    const int iE = (g == 2 * q) ? 0 : ((g == 2 * q + 1) ? 1 : -1);   // which element is the unit entry
+    const uint32_t ypub = a_y + 8u * (uint32_t)(g * 4 + q);
+    const uint32_t oE1 = a_stage + lane_col, oE2 = a_stage + 8u * 128u + lane_col;
+    const uint32_t oD = a_stage + o_D + lane_col, oT = a_stage + o_J + 8u * (uint32_t)(m * 128) + lane_col;
+    const uint32_t xl = 8u * (uint32_t)p.x_off + lane_col;
+    int s3 = 0;
+    for (int i = 0; i < n_my; ++i) {
+      const uint32_t a_z = a_grp + 8u * (uint32_t)(s3 * p.zpad);
+      const uint32_t a_p = a_prep + 8u * (uint32_t)((i & 1) * kU8Prep);
+      const uint32_t a_c = a_p + 8u * 256u;
+      mbar_wait(mb_ready + 8 * (i & 1), (uint32_t)((i >> 1) & 1));
+      double A[4][2];
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) A[kt][nt] = lds_f64<0>(a_p + 8u * (uint32_t)((kt * 2 + nt) * 32 + lane));
+      int M, n_sub;
+      lds_v2u32(a_p + 8u * 276u, M, n_sub);
+      double bX[4], bE[4], tE[4], tX[4];
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) bX[i4] = lds_f64<0>(a_z + xl + U8_OFF(i4));
+      {
+        const double cM = lds_f64<0>(a_c + 8u * (uint32_t)M);
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          bE[i4] = (i4 == iE) ? 1.0 : 0.0;
+          tE[i4] = (i4 == iE) ? cM : 0.0;
+          tX[i4] = cM * bX[i4];
+        }
+      }
+      bar_sync(xbar, nx);   // the exchange buffers are free (readers of the previous knot are done)
+      for (int sub = 0; sub < n_sub; ++sub) {
+        if (sub > 0) {
+          const double cM = lds_f64<0>(a_c + 8u * (uint32_t)M);
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            bE[i4] = tE[i4];
+            bX[i4] = tX[i4];
+            tE[i4] *= cM;
+            tX[i4] *= cM;
+          }
+          bar_sync(xbar, nx);
+        }
+        int kq = M - 1;
+        if (sub == 0) {
+          for (; kq >= 1; kq -= 2) {
+            u8_step_ex<0, true>(tE, tX, bE, bX, A, iE, ypub, a_c + 8u * kq, xbar, nx);
+            u8_step_ex<1, true>(tE, tX, bE, bX, A, iE, ypub, a_c + 8u * kq - 8u, xbar, nx);
+          }
+          if (kq == 0) u8_step_ex<0, true>(tE, tX, bE, bX, A, iE, ypub, a_c, xbar, nx);
+        } else {
+          for (; kq >= 1; kq -= 2) {
+            u8_step_ex<0, false>(tE, tX, bE, bX, A, iE, ypub, a_c + 8u * kq, xbar, nx);
+            u8_step_ex<1, false>(tE, tX, bE, bX, A, iE, ypub, a_c + 8u * kq - 8u, xbar, nx);
+          }
+          if (kq == 0) u8_step_ex<0, false>(tE, tX, bE, bX, A, iE, ypub, a_c, xbar, nx);
+        }
+      }
+      // ---- d/d dt = -G(u) E x : one more generator product on the state tile --------------------
+      double dT[2][2];
+      u8_mma(dT, tX, A);
+      double xn[4];
+      if (p.delta) {
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) xn[i4] = lds_f64<0>(a_z + 8u * p.D + xl + U8_OFF(i4));
+      }
+      mbar_wait(mb_free, (uint32_t)(i & 1));
+      // -E = -[[P, -Q], [Q, P]]: own column g, mirrored column g + 8
+      sts_f64<0>(oE1, -tE[0]);   sts_f64<8>(oE1, -tE[1]);   sts_f64<64>(oE1, -tE[2]);  sts_f64<72>(oE1, -tE[3]);
+      sts_f64<64>(oE2, -tE[0]);  sts_f64<72>(oE2, -tE[1]);  sts_f64<0>(oE2, tE[2]);    sts_f64<8>(oE2, tE[3]);
+      if (p.delta) {
+        sts_f64<0>(oD, xn[0] - tX[0]);   sts_f64<8>(oD, xn[1] - tX[1]);
+        sts_f64<64>(oD, xn[2] - tX[2]);  sts_f64<72>(oD, xn[3] - tX[3]);
+      }
+      sts_f64<0>(oT, -dT[0][0]);   sts_f64<8>(oT, -dT[0][1]);
+      sts_f64<64>(oT, -dT[1][0]);  sts_f64<72>(oT, -dT[1][1]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mb_staged);
+      s3 = s3 == 2 ? 0 : s3 + 1;
+    }
+    return;
+  }
+
+  {
+    // ---- jets of drives jd0 = 2 jw and jd1 = 2 jw + 1 ---------------------------------------------
+    const int jw = role - 2;
+    const int jd0 = 2 * jw, jd1 = 2 * jw + 1;
+    const bool two = jd1 < m;
+    double ev[2][4][W];
+    uint32_t yad[2][4][W];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int jd = a == 0 ? jd0 : (two ? jd1 : m);   // drive m is the all-zero dummy
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        const int r = 8 * (i4 >> 1) + 2 * q + (i4 & 1);
+#pragma unroll
+        for (int ww = 0; ww < W; ++ww) {
+          const EllEntry en = p.ell[((size_t)jd * 16 + r) * W + ww];
+          ev[a][i4][ww] = en.val;
+          yad[a][i4][ww] = a_y + 8u * (uint32_t)((2 * (en.idx >> 3) + (en.idx & 1)) * 32 + g * 4 + ((en.idx & 7) >> 1));
+        }
+      }
+    }
+    const uint32_t oJ0 = a_stage + o_J + 8u * (uint32_t)(jd0 * 128) + lane_col;
+    const uint32_t oJ1 = a_stage + o_J + 8u * (uint32_t)(jd1 * 128) + lane_col;
+    for (int i = 0; i < n_my; ++i) {
+      const uint32_t a_p = a_prep + 8u * (uint32_t)((i & 1) * kU8Prep);
+      const uint32_t a_c = a_p + 8u * 256u;
+      mbar_wait(mb_ready + 8 * (i & 1), (uint32_t)((i >> 1) & 1));
+      double A[4][2];
+#pragma unroll
+      for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) A[kt][nt] = lds_f64<0>(a_p + 8u * (uint32_t)((kt * 2 + nt) * 32 + lane));
+      int M, n_sub;
+      lds_v2u32(a_p + 8u * 276u, M, n_sub);
+      double t[2][4], bJ[2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) t[a][i4] = bJ[a][i4] = 0.0;
+      bar_sync(xbar, nx);
+      for (int sub = 0; sub < n_sub; ++sub) {
+        if (sub > 0) {
+          const double cM = lds_f64<0>(a_c + 8u * (uint32_t)M);
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              bJ[a][i4] = t[a][i4];
+              t[a][i4] *= cM;
+            }
+          bar_sync(xbar, nx);
+        }
+        int kq = M - 1;
+        if (sub == 0) {
+          // the jets start from zero: the first step is the coupling term alone
+          u8_step_jets<W, 0, true, true>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
+          --kq;
+          for (; kq >= 1; kq -= 2) {
+            u8_step_jets<W, 1, true, false>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
+            u8_step_jets<W, 0, true, false>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
+          }
+          if (kq == 0) u8_step_jets<W, 1, true, false>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
+        } else {
+          for (; kq >= 1; kq -= 2) {
+            u8_step_jets<W, 0, false, false>(t, bJ, A, ev, yad, a_c + 8u * kq, two, xbar, nx);
+            u8_step_jets<W, 1, false, false>(t, bJ, A, ev, yad, a_c + 8u * kq - 8u, two, xbar, nx);
+          }
+          if (kq == 0) u8_step_jets<W, 0, false, false>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
+        }
+      }
+      mbar_wait(mb_free, (uint32_t)(i & 1));
+      sts_f64<0>(oJ0, -t[0][0]);   sts_f64<8>(oJ0, -t[0][1]);
+      sts_f64<64>(oJ0, -t[0][2]);  sts_f64<72>(oJ0, -t[0][3]);
+      if (two) {
+        sts_f64<0>(oJ1, -t[1][0]);   sts_f64<8>(oJ1, -t[1][1]);
+        sts_f64<64>(oJ1, -t[1][2]);  sts_f64<72>(oJ1, -t[1][3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(mb_staged);
+    }
+  }
+}
+
+// Shared-memory layout (doubles; every region 16-byte aligned).  CTA-wide: fragment tables
+// [(m+1) 256], norms.  Per group: slab x3 | prepared knot x2 | X exchange x2 | stage
+// [E x8 (2048) | jets, d/d dt, ones ((m+2) 128) | delta (128)] | mbarriers.
+inline size_t u8_layout(U8Params& q, int gpc) {
+  auto even = [](int v) { return (v + 1) & ~1; };
+  q.o_norm = (q.m + 1) * 256;
+  q.o_grp = q.o_norm + even(q.m + 1);
+  q.zpad = even(q.zlen);
+  q.o_prep = 3 * q.zpad;
+  q.o_y = q.o_prep + 2 * kU8Prep;
+  q.o_stage = q.o_y + 2 * 128;
+  q.o_mbar = q.o_stage + 2048 + (q.m + 2) * 128 + 128;
+  q.grp_stride = q.o_mbar + 8;
+  return sizeof(double) * ((size_t)q.o_grp + (size_t)gpc * q.grp_stride);
+}
+
+using U8Kernel = void (*)(U8Params);
+inline U8Kernel u8_kernel(int W) {
+  return W == 1 ? knot_u8_kernel<1> : (W == 2 ? knot_u8_kernel<2> : knot_u8_kernel<4>);
+}
+
+}  // namespace pb2

@@ -19,6 +19,7 @@
 #include "../../include/piccolo_b200.h"
 #include "knot_generic.cuh"
 #include "knot_dmma.cuh"
+#include "knot_u8.cuh"
 
 namespace {
 
@@ -90,6 +91,7 @@ struct pb2_handle {
   long long* dTrace = nullptr;
   long long* dTrace2 = nullptr;
   int n_sm = 148, gpc_default = 3, gpc_override = 0;
+  bool u8_ok = false;
   pb2::EllEntry* dEll = nullptr;
   // staging for host-pointer calls
   double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
@@ -118,7 +120,28 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
   if (h->nk() <= 0) return PB2_OK;
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.delta = ddelta; p.jac = djac;
-  if (h->alg == PB2_ALG_DMMA) {
+  const bool aligned16 = ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0);
+  if (h->alg == PB2_ALG_DMMA && h->u8_ok && djac && aligned16 && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
+    // the 3-qubit unitary shape: warp-specialised kernel (producer warp + (E,X) warp + jet warps)
+    const pb2::DmmaPlan& pl = h->plan;
+    pb2::U8Params q{};
+    q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
+    q.nnz_jac = p.nnz_jac; q.max_sub = 4096; q.nk = (int)h->nk();
+    q.zlen = p.D + p.x_off + 128;
+    q.gw = 2 + (p.m + 1) / 2;
+    q.Gfrag = h->dGfrag; q.ell = h->dEll; q.norms = h->dNorms;
+    q.Z = dZ; q.delta = ddelta; q.jac = djac;
+    int maxg = std::min(pb2::kU8MaxGroups, pb2::kU8MaxThreads / (32 * q.gw));
+    while (maxg > 1 && pb2::u8_layout(q, maxg) > kSmemLimit) --maxg;
+    const int per_sm = (q.nk + h->n_sm - 1) / h->n_sm;
+    q.gpc = std::max(1, std::min(maxg, h->gpc_override > 0 ? h->gpc_override : per_sm));
+    const int blocks = std::min(h->n_sm, (q.nk + q.gpc - 1) / q.gpc);
+    const size_t smem = pb2::u8_layout(q, q.gpc);
+    if (smem > kSmemLimit) return fail(PB2_EINVAL, "u8 resjac: knot column too large for the shared-memory staging");
+    pb2::u8_kernel(pl.W)<<<blocks, 32 * q.gw * q.gpc, smem, st>>>(q);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("u8 resjac launch: ") + cudaGetErrorString(e));
+  } else if (h->alg == PB2_ALG_DMMA) {
     // residual-only calls carry just the state columns; anything with a Jacobian carries the
     // propagator columns and one jet per drive as well
     const bool jets = djac != nullptr;
@@ -340,6 +363,10 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     PB2_CUDA_H(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, d.device));
     if (const char* env = std::getenv("PB2_GPC")) h->gpc_override = std::atoi(env);
+    h->u8_ok = h->plan.iso && d.b == 16 && d.n_b == 8 && d.m >= 1 && d.m <= 6 && !std::getenv("PB2_NO_U8");
+    if (h->u8_ok)
+      PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8_kernel(h->plan.W), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemLimit));
 #ifdef PB2_TRACE
     PB2_CUDA_H(cudaMalloc(&h->dTrace, 8 * 16 * 8 * sizeof(long long)));
     PB2_CUDA_H(cudaMemset(h->dTrace, 0, 8 * 16 * 8 * sizeof(long long)));
