@@ -30,14 +30,17 @@ namespace pb2 {
 struct U8Params {
   int m, D, x_off, dt_off, u_off, nnz_jac, max_sub, gpc, nk, zlen;
   int gw;                // warps per group: producer + (E,X) + ceil(m/2) jet warps
+  int stagger;           // cycles by which group g delays its first knot (g * stagger): de-phases the groups
   // shared-memory layout in doubles (u8_layout)
-  int o_norm, o_grp, grp_stride, zpad, o_prep, o_y, o_stage, o_mbar;
+  int o_norm, o_tab, o_grp, grp_stride, zpad, o_prep, o_y, o_stage, o_mbar;
+  const double* tab;     // theta_0..19 | 1/0! .. 1/19!  (40 doubles)
   const double* Gfrag;   // (m+1) * 256 doubles, B-fragment order
   const EllEntry* ell;   // (m+1) * 16 * W   (drive m = all-zero dummy)
   const double* norms;   // m+1
   const double* Z;
   double* delta;         // may be null
   double* jac;
+  long long* trace;      // debug build only: clock stamps of block 0
 };
 
 constexpr int kU8Prep = 280;        // doubles per prepared knot: G(u) frags 256 | a_k 20 | M, n_sub | pad
@@ -130,6 +133,12 @@ __device__ __forceinline__ void u8_step_jets(double (&t)[2][4], const double (&b
     }
 }
 
+#ifdef PB2_TRACE
+#define U8_STAMP(i) do { if (blockIdx.x == 0 && lane == 0 && i_knot < 4) p.trace[((wcta * 4 + i_knot) * 8) + (i)] = clock64(); } while (0)
+#else
+#define U8_STAMP(i) do { } while (0)
+#endif
+
 template <int W>
 __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_constant__ U8Params p) {
   extern __shared__ __align__(16) double u8_smem[];
@@ -146,57 +155,81 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
   const uint32_t mb_zfull = a_mbar, mb_ready = a_mbar + 24, mb_staged = a_mbar + 40, mb_free = a_mbar + 48;
   const uint32_t o_J = 8u * 2048u, o_D = 8u * (2048u + (uint32_t)(m + 2) * 128u);   // inside the stage
 
+  const int TG = gridDim.x * p.gpc, gg = group * gridDim.x + blockIdx.x;
+  const int n_my = gg < p.nk ? (p.nk - gg + TG - 1) / TG : 0;
+  const uint32_t zbytes = (uint32_t)p.zlen * 8u;
+
   // ---- once per CTA ------------------------------------------------------------------------------
-  for (int e = threadIdx.x; e < (m + 1) * 256; e += blockDim.x) u8_smem[e] = p.Gfrag[e];
-  for (int e = threadIdx.x; e <= m; e += blockDim.x) u8_smem[p.o_norm + e] = p.norms[e];
-  {
-    double* ones = u8_smem + p.o_grp + group * p.grp_stride + p.o_stage + 2048 + (m + 1) * 128;
-    for (int e = wg * 32 + lane; e < 128; e += 32 * gw) ones[e] = 1.0;
-  }
-  if (wg == 0 && lane == 0) {
+  // the producer lane first arms its group's mbarriers and starts the first two slab loads, so that
+  // the HBM latency of the slabs overlaps the table fill below
+  // programmatic dependent launch: let the next grid on the stream start its own prologue as
+  // SMs drain, and do not touch trajectory / output memory before the previous grid is complete
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (role == 0 && lane == 0) {
     for (int i = 0; i < 3; ++i) mbar_init(mb_zfull + 8 * i, 1);
     mbar_init(mb_ready, 1);
     mbar_init(mb_ready + 8, 1);
     mbar_init(mb_staged, ncw);
     mbar_init(mb_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int i = 0; i < 2 && i < n_my; ++i) {
+      mbar_expect_tx(mb_zfull + 8 * i, zbytes);
+      bulk_g2s(a_grp + 8u * (uint32_t)(i * p.zpad), p.Z + (size_t)(gg + i * TG) * p.D, zbytes, mb_zfull + 8 * i);
+    }
+    mbar_arrive(mb_free);   // the stage starts free
+  }
+  for (int e = threadIdx.x; e < (m + 1) * 256; e += blockDim.x) u8_smem[e] = p.Gfrag[e];
+  for (int e = threadIdx.x; e <= m; e += blockDim.x) u8_smem[p.o_norm + e] = p.norms[e];
+  for (int e = threadIdx.x; e < 40; e += blockDim.x) u8_smem[p.o_tab + e] = p.tab[e];
+  {
+    double* ones = u8_smem + p.o_grp + group * p.grp_stride + p.o_stage + 2048 + (m + 1) * 128;
+    for (int e = wg * 32 + lane; e < 128; e += 32 * gw) ones[e] = 1.0;
   }
   __syncthreads();
 
-  const int TG = gridDim.x * p.gpc, gg = group * gridDim.x + blockIdx.x;
-  const int n_my = gg < p.nk ? (p.nk - gg + TG - 1) / TG : 0;
-  const uint32_t zbytes = (uint32_t)p.zlen * 8u;
-
   if (role == 0) {
     // =============================== producer warp ===============================================
-    if (lane == 0) {
-      for (int i = 0; i < 2 && i < n_my; ++i) {
-        mbar_expect_tx(mb_zfull + 8 * i, zbytes);
-        bulk_g2s(a_grp + 8u * (uint32_t)(i * p.zpad), p.Z + (size_t)(gg + i * TG) * p.D, zbytes, mb_zfull + 8 * i);
-      }
-      mbar_arrive(mb_free);   // the stage starts free
-    }
-    const double th_l = c_theta[lane <= kMaxDeg ? lane : kMaxDeg];
-    const double if_l = c_invfact[lane <= kMaxDeg ? lane : kMaxDeg];
-    const double th_max = c_theta[kMaxDeg];
+    const double th_l = u8_smem[p.o_tab + (lane <= kMaxDeg ? lane : kMaxDeg)];
+    const double if_l = u8_smem[p.o_tab + 20 + (lane <= kMaxDeg ? lane : kMaxDeg)];
+    const double th_max = u8_smem[p.o_tab + kMaxDeg];
+    const long long t_begin = clock64();
     int s3 = 0;
     for (int i = 0; i <= n_my; ++i) {
       if (i < n_my) {
         // ---- prepare knot i: G(u), Taylor degree, coefficients ------------------------------------
         const uint32_t a_z = a_grp + 8u * (uint32_t)(s3 * p.zpad);
         const uint32_t a_p = a_prep + 8u * (uint32_t)((i & 1) * kU8Prep);
+        const int i_knot = i;
+        U8_STAMP(0);
         mbar_wait(mb_zfull + 8 * s3, (uint32_t)((i / 3) & 1));
+        U8_STAMP(1);
+        double uj[6], nj[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          uj[j] = 0.0;
+          nj[j] = 0.0;
+          if (j < m) {
+            uj[j] = lds_f64<0>(a_z + 8u * (uint32_t)(p.u_off + j));
+            nj[j] = lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_norm + 1 + j));
+          }
+        }
+        double dt = lds_f64<0>(a_z + 8u * p.dt_off);
+        double nrm = lds_f64<0>(a_cG + 8u * p.o_norm);
         double acc[8];
 #pragma unroll
         for (int s = 0; s < 8; ++s) acc[s] = lds_f64<0>(a_cG + 8u * (uint32_t)(s * 32 + lane));
-        double dt = lds_f64<0>(a_z + 8u * p.dt_off);
-        double nrm = lds_f64<0>(a_cG + 8u * p.o_norm);
-        for (int j = 0; j < m; ++j) {
-          const double uj = lds_f64<0>(a_z + 8u * (uint32_t)(p.u_off + j));
-          nrm = fma(fabs(uj), lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_norm + 1 + j)), nrm);
-          const uint32_t a_gj = a_cG + 8u * (uint32_t)((1 + j) * 256 + lane);
 #pragma unroll
-          for (int s = 0; s < 8; ++s) acc[s] = fma(uj, lds_f64<0>(a_gj + 256u * s), acc[s]);
+        for (int j = 0; j < 6; ++j) {
+          if (j < m) {
+            const uint32_t a_gj = a_cG + 8u * (uint32_t)((1 + j) * 256 + lane);
+            double gv[8];
+#pragma unroll
+            for (int s = 0; s < 8; ++s) gv[s] = lds_f64<0>(a_gj + 256u * s);
+#pragma unroll
+            for (int s = 0; s < 8; ++s) acc[s] = fma(uj[j], gv[s], acc[s]);
+            nrm = fma(fabs(uj[j]), nj[j], nrm);
+          }
         }
 #pragma unroll
         for (int s = 0; s < 8; ++s) sts_f64<0>(a_p + 8u * (uint32_t)(s * 32 + lane), acc[s]);
@@ -225,12 +258,21 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         if (lane <= kMaxDeg) sts_f64<0>(a_p + 8u * 256u + 8u * lane, lane <= M ? if_l * pw : 0.0);
         if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_p + 8u * 276u), "r"(M), "r"(n_sub) : "memory");
         __syncwarp();
+        if (i == 0 && p.stagger > 0) {
+          // groups that run in lockstep all leave the tensor pipe idle at the same time
+          const long long t_end = t_begin + (long long)group * p.stagger;
+          while (clock64() < t_end) { }
+        }
         if (lane == 0) mbar_arrive(mb_ready + 8 * (i & 1));
+        U8_STAMP(2);
       }
       if (i >= 1) {
         // ---- finish knot i-1: replicate the propagator block, one bulk store per output --------
         const int kprev = gg + (i - 1) * TG;
+        const int i_knot = i - 1;
+        U8_STAMP(3);
         mbar_wait(mb_staged, (uint32_t)((i - 1) & 1));
+        U8_STAMP(4);
         double2 v[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) v[jj] = lds_f64x2<0>(a_stage + 16u * (uint32_t)(lane + 32 * jj));
@@ -245,6 +287,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
           if (p.delta) bulk_s2g(p.delta + (size_t)kprev * 128, a_stage + o_D, 1024u);
           bulk_commit();
         }
+        U8_STAMP(5);
       }
       if (lane == 0) {
         // slab (i+2)%3 held knot i-1, which is finished
@@ -257,6 +300,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         if (i >= 1) {
           bulk_wait_read0();        // the stage has been read: the compute warps may refill it
           mbar_arrive(mb_free);
+          { const int i_knot = i - 1; U8_STAMP(6); }
         }
       }
       __syncwarp();
@@ -280,7 +324,10 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
       const uint32_t a_z = a_grp + 8u * (uint32_t)(s3 * p.zpad);
       const uint32_t a_p = a_prep + 8u * (uint32_t)((i & 1) * kU8Prep);
       const uint32_t a_c = a_p + 8u * 256u;
+      const int i_knot = i;
+      U8_STAMP(0);
       mbar_wait(mb_ready + 8 * (i & 1), (uint32_t)((i >> 1) & 1));
+      U8_STAMP(1);
       double A[4][2];
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt)
@@ -288,47 +335,48 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         for (int nt = 0; nt < 2; ++nt) A[kt][nt] = lds_f64<0>(a_p + 8u * (uint32_t)((kt * 2 + nt) * 32 + lane));
       int M, n_sub;
       lds_v2u32(a_p + 8u * 276u, M, n_sub);
-      double bX[4], bE[4], tE[4], tX[4];
+      double bX[4], tE[4], tX[4];
 #pragma unroll
       for (int i4 = 0; i4 < 4; ++i4) bX[i4] = lds_f64<0>(a_z + xl + U8_OFF(i4));
       {
         const double cM = lds_f64<0>(a_c + 8u * (uint32_t)M);
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
-          bE[i4] = (i4 == iE) ? 1.0 : 0.0;
           tE[i4] = (i4 == iE) ? cM : 0.0;
           tX[i4] = cM * bX[i4];
         }
       }
       bar_sync(xbar, nx);   // the exchange buffers are free (readers of the previous knot are done)
-      for (int sub = 0; sub < n_sub; ++sub) {
-        if (sub > 0) {
-          const double cM = lds_f64<0>(a_c + 8u * (uint32_t)M);
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            bE[i4] = tE[i4];
-            bX[i4] = tX[i4];
-            tE[i4] *= cM;
-            tX[i4] *= cM;
-          }
-          bar_sync(xbar, nx);
-        }
+      U8_STAMP(2);
+      {
         int kq = M - 1;
-        if (sub == 0) {
-          for (; kq >= 1; kq -= 2) {
-            u8_step_ex<0, true>(tE, tX, bE, bX, A, iE, ypub, a_c + 8u * kq, xbar, nx);
-            u8_step_ex<1, true>(tE, tX, bE, bX, A, iE, ypub, a_c + 8u * kq - 8u, xbar, nx);
-          }
-          if (kq == 0) u8_step_ex<0, true>(tE, tX, bE, bX, A, iE, ypub, a_c, xbar, nx);
-        } else {
-          for (; kq >= 1; kq -= 2) {
-            u8_step_ex<0, false>(tE, tX, bE, bX, A, iE, ypub, a_c + 8u * kq, xbar, nx);
-            u8_step_ex<1, false>(tE, tX, bE, bX, A, iE, ypub, a_c + 8u * kq - 8u, xbar, nx);
-          }
-          if (kq == 0) u8_step_ex<0, false>(tE, tX, bE, bX, A, iE, ypub, a_c, xbar, nx);
+        for (; kq >= 1; kq -= 2) {
+          u8_step_ex<0, true>(tE, tX, bX, bX, A, iE, ypub, a_c + 8u * kq, xbar, nx);
+          u8_step_ex<1, true>(tE, tX, bX, bX, A, iE, ypub, a_c + 8u * kq - 8u, xbar, nx);
         }
+        if (kq == 0) u8_step_ex<0, true>(tE, tX, bX, bX, A, iE, ypub, a_c, xbar, nx);
+      }
+      // further sub-steps (||dt G|| beyond the largest tabulated radius: rare), general B
+      for (int sub = 1; sub < n_sub; ++sub) {
+        double bE2[4], bX2[4];
+        const double cM = lds_f64<0>(a_c + 8u * (uint32_t)M);
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          bE2[i4] = tE[i4];
+          bX2[i4] = tX[i4];
+          tE[i4] *= cM;
+          tX[i4] *= cM;
+        }
+        bar_sync(xbar, nx);
+        int kq = M - 1;
+        for (; kq >= 1; kq -= 2) {
+          u8_step_ex<0, false>(tE, tX, bE2, bX2, A, iE, ypub, a_c + 8u * kq, xbar, nx);
+          u8_step_ex<1, false>(tE, tX, bE2, bX2, A, iE, ypub, a_c + 8u * kq - 8u, xbar, nx);
+        }
+        if (kq == 0) u8_step_ex<0, false>(tE, tX, bE2, bX2, A, iE, ypub, a_c, xbar, nx);
       }
       // ---- d/d dt = -G(u) E x : one more generator product on the state tile --------------------
+      U8_STAMP(3);
       double dT[2][2];
       u8_mma(dT, tX, A);
       double xn[4];
@@ -336,7 +384,9 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) xn[i4] = lds_f64<0>(a_z + 8u * p.D + xl + U8_OFF(i4));
       }
+      U8_STAMP(4);
       mbar_wait(mb_free, (uint32_t)(i & 1));
+      U8_STAMP(5);
       // -E = -[[P, -Q], [Q, P]]: own column g, mirrored column g + 8
       sts_f64<0>(oE1, -tE[0]);   sts_f64<8>(oE1, -tE[1]);   sts_f64<64>(oE1, -tE[2]);  sts_f64<72>(oE1, -tE[3]);
       sts_f64<64>(oE2, -tE[0]);  sts_f64<72>(oE2, -tE[1]);  sts_f64<0>(oE2, tE[2]);    sts_f64<8>(oE2, tE[3]);
@@ -346,9 +396,9 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
       }
       sts_f64<0>(oT, -dT[0][0]);   sts_f64<8>(oT, -dT[0][1]);
       sts_f64<64>(oT, -dT[1][0]);  sts_f64<72>(oT, -dT[1][1]);
-      fence_proxy_async();
-      __syncwarp();
+      __syncwarp();   // the producer orders these writes before its bulk store (fence.proxy.async after the acquire)
       if (lane == 0) mbar_arrive(mb_staged);
+      U8_STAMP(6);
       s3 = s3 == 2 ? 0 : s3 + 1;
     }
     return;
@@ -380,7 +430,10 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
     for (int i = 0; i < n_my; ++i) {
       const uint32_t a_p = a_prep + 8u * (uint32_t)((i & 1) * kU8Prep);
       const uint32_t a_c = a_p + 8u * 256u;
+      const int i_knot = i;
+      U8_STAMP(0);
       mbar_wait(mb_ready + 8 * (i & 1), (uint32_t)((i >> 1) & 1));
+      U8_STAMP(1);
       double A[4][2];
 #pragma unroll
       for (int kt = 0; kt < 4; ++kt)
@@ -388,52 +441,53 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         for (int nt = 0; nt < 2; ++nt) A[kt][nt] = lds_f64<0>(a_p + 8u * (uint32_t)((kt * 2 + nt) * 32 + lane));
       int M, n_sub;
       lds_v2u32(a_p + 8u * 276u, M, n_sub);
-      double t[2][4], bJ[2][4];
+      double t[2][4];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) t[a][i4] = bJ[a][i4] = 0.0;
+        for (int i4 = 0; i4 < 4; ++i4) t[a][i4] = 0.0;
       bar_sync(xbar, nx);
-      for (int sub = 0; sub < n_sub; ++sub) {
-        if (sub > 0) {
-          const double cM = lds_f64<0>(a_c + 8u * (uint32_t)M);
-#pragma unroll
-          for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              bJ[a][i4] = t[a][i4];
-              t[a][i4] *= cM;
-            }
-          bar_sync(xbar, nx);
+      U8_STAMP(2);
+      {
+        // the jets start from zero: the first step is the coupling term alone
+        int kq = M - 2;
+        u8_step_jets<W, 0, true, true>(t, t, A, ev, yad, a_c, two, xbar, nx);
+        for (; kq >= 1; kq -= 2) {
+          u8_step_jets<W, 1, true, false>(t, t, A, ev, yad, a_c, two, xbar, nx);
+          u8_step_jets<W, 0, true, false>(t, t, A, ev, yad, a_c, two, xbar, nx);
         }
-        int kq = M - 1;
-        if (sub == 0) {
-          // the jets start from zero: the first step is the coupling term alone
-          u8_step_jets<W, 0, true, true>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
-          --kq;
-          for (; kq >= 1; kq -= 2) {
-            u8_step_jets<W, 1, true, false>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
-            u8_step_jets<W, 0, true, false>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
-          }
-          if (kq == 0) u8_step_jets<W, 1, true, false>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
-        } else {
-          for (; kq >= 1; kq -= 2) {
-            u8_step_jets<W, 0, false, false>(t, bJ, A, ev, yad, a_c + 8u * kq, two, xbar, nx);
-            u8_step_jets<W, 1, false, false>(t, bJ, A, ev, yad, a_c + 8u * kq - 8u, two, xbar, nx);
-          }
-          if (kq == 0) u8_step_jets<W, 0, false, false>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
-        }
+        if (kq == 0) u8_step_jets<W, 1, true, false>(t, t, A, ev, yad, a_c, two, xbar, nx);
       }
+      for (int sub = 1; sub < n_sub; ++sub) {
+        double bJ[2][4];
+        const double cM = lds_f64<0>(a_c + 8u * (uint32_t)M);
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            bJ[a][i4] = t[a][i4];
+            t[a][i4] *= cM;
+          }
+        bar_sync(xbar, nx);
+        int kq = M - 1;
+        for (; kq >= 1; kq -= 2) {
+          u8_step_jets<W, 0, false, false>(t, bJ, A, ev, yad, a_c + 8u * kq, two, xbar, nx);
+          u8_step_jets<W, 1, false, false>(t, bJ, A, ev, yad, a_c + 8u * kq - 8u, two, xbar, nx);
+        }
+        if (kq == 0) u8_step_jets<W, 0, false, false>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
+      }
+      U8_STAMP(4);
       mbar_wait(mb_free, (uint32_t)(i & 1));
+      U8_STAMP(5);
       sts_f64<0>(oJ0, -t[0][0]);   sts_f64<8>(oJ0, -t[0][1]);
       sts_f64<64>(oJ0, -t[0][2]);  sts_f64<72>(oJ0, -t[0][3]);
       if (two) {
         sts_f64<0>(oJ1, -t[1][0]);   sts_f64<8>(oJ1, -t[1][1]);
         sts_f64<64>(oJ1, -t[1][2]);  sts_f64<72>(oJ1, -t[1][3]);
       }
-      fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(mb_staged);
+      U8_STAMP(6);
     }
   }
 }
@@ -444,7 +498,8 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
 inline size_t u8_layout(U8Params& q, int gpc) {
   auto even = [](int v) { return (v + 1) & ~1; };
   q.o_norm = (q.m + 1) * 256;
-  q.o_grp = q.o_norm + even(q.m + 1);
+  q.o_tab = q.o_norm + even(q.m + 1);
+  q.o_grp = q.o_tab + 40;
   q.zpad = even(q.zlen);
   q.o_prep = 3 * q.zpad;
   q.o_y = q.o_prep + 2 * kU8Prep;

@@ -88,10 +88,13 @@ struct pb2_handle {
   pb2::DmmaPlan plan;          // tensor-core path tables (host copy) and their device mirrors
   double* dGfrag = nullptr;
   double* dNorms = nullptr;
+  double* dTab = nullptr;
   long long* dTrace = nullptr;
   long long* dTrace2 = nullptr;
   int n_sm = 148, gpc_default = 3, gpc_override = 0;
   bool u8_ok = false;
+  int stagger = 0;
+  int pdl = 1;
   pb2::EllEntry* dEll = nullptr;
   // staging for host-pointer calls
   double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
@@ -129,8 +132,9 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.nnz_jac = p.nnz_jac; q.max_sub = 4096; q.nk = (int)h->nk();
     q.zlen = p.D + p.x_off + 128;
     q.gw = 2 + (p.m + 1) / 2;
-    q.Gfrag = h->dGfrag; q.ell = h->dEll; q.norms = h->dNorms;
-    q.Z = dZ; q.delta = ddelta; q.jac = djac;
+    q.stagger = h->stagger;
+    q.Gfrag = h->dGfrag; q.ell = h->dEll; q.norms = h->dNorms; q.tab = h->dTab;
+    q.Z = dZ; q.delta = ddelta; q.jac = djac; q.trace = h->dTrace2;
     int maxg = std::min(pb2::kU8MaxGroups, pb2::kU8MaxThreads / (32 * q.gw));
     while (maxg > 1 && pb2::u8_layout(q, maxg) > kSmemLimit) --maxg;
     const int per_sm = (q.nk + h->n_sm - 1) / h->n_sm;
@@ -138,8 +142,18 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     const int blocks = std::min(h->n_sm, (q.nk + q.gpc - 1) / q.gpc);
     const size_t smem = pb2::u8_layout(q, q.gpc);
     if (smem > kSmemLimit) return fail(PB2_EINVAL, "u8 resjac: knot column too large for the shared-memory staging");
-    pb2::u8_kernel(pl.W)<<<blocks, 32 * q.gw * q.gpc, smem, st>>>(q);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(32 * q.gw * q.gpc);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, pb2::u8_kernel(pl.W), q);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("u8 resjac launch: ") + cudaGetErrorString(e));
   } else if (h->alg == PB2_ALG_DMMA) {
     // residual-only calls carry just the state columns; anything with a Jacobian carries the
@@ -359,10 +373,18 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     invfact[0] = 1.0;
     for (int q = 1; q <= pb2::kMaxDeg; ++q) invfact[q] = invfact[q - 1] / (double)q;
     PB2_CUDA_H(cudaMemcpyToSymbol(pb2::c_invfact, invfact, sizeof(invfact)));
+    {
+      double tab[40] = {0};
+      for (int q = 0; q <= pb2::kMaxDeg; ++q) { tab[q] = theta[q]; tab[20 + q] = invfact[q]; }
+      PB2_CUDA_H(cudaMalloc(&h->dTab, sizeof(tab)));
+      PB2_CUDA_H(cudaMemcpy(h->dTab, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    }
     PB2_CUDA_H(cudaFuncSetAttribute(pb2::dmma_kernel(h->plan.NT, h->plan.W),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     PB2_CUDA_H(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, d.device));
     if (const char* env = std::getenv("PB2_GPC")) h->gpc_override = std::atoi(env);
+    if (const char* env = std::getenv("PB2_STAGGER")) h->stagger = std::atoi(env);
+    if (const char* env = std::getenv("PB2_PDL")) h->pdl = std::atoi(env);
     h->u8_ok = h->plan.iso && d.b == 16 && d.n_b == 8 && d.m >= 1 && d.m <= 6 && !std::getenv("PB2_NO_U8");
     if (h->u8_ok)
       PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8_kernel(h->plan.W), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -393,6 +415,7 @@ void pb2_destroy(pb2_handle* h) {
   if (h->dGfrag) cudaFree(h->dGfrag);
   if (h->dEll) cudaFree(h->dEll);
   if (h->dNorms) cudaFree(h->dNorms);
+  if (h->dTab) cudaFree(h->dTab);
   if (h->dTrace) cudaFree(h->dTrace);
   for (double* p : {h->hZ, h->hDelta, h->hJac, h->hMu, h->hHess})
     if (p) cudaFreeHost(p);

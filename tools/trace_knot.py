@@ -18,13 +18,26 @@ lib = pb.load_library()
 lib.pb2_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 assert lib.pb2_debug_trace(B._h, out.ctypes.data) == 0
 T = out.reshape(8, 16, 8)
-t0 = T[T > 0].min()
+t0 = T[T > 0].min() if (T > 0).any() else 0
 names = ["start", "slab", "prebar", "postbar", "loaded", "horner", "staged", "postbar2"]
 for it in range(8):
     for w in range(16):
         if T[it, w].max() > 0:
             print(f"knot {it} warp {w:2d}: " + " ".join(f"{n}={int(v - t0):6d}" for n, v in zip(names, T[it, w])))
 
+if B.algorithm == "dmma" and p.b == 16 and p.n_b == 8 and not os.environ.get("PB2_NO_U8"):
+    out2 = np.zeros(16 * 20 * 4, dtype=np.int64)
+    lib.pb2_debug_trace2.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    assert lib.pb2_debug_trace2(B._h, out2.ctypes.data) == 0
+    T2 = out2[:16 * 4 * 8].reshape(16, 4, 8)
+    t0 = T2[T2 > 0].min()
+    print("u8 kernel, block 0: warp, knot, stamps (producer: wait-z, got-z, ready | staged-wait, staged, stored, freed;"
+          " compute: start, ready, horner-start, horner-end, pre-free, free, staged)")
+    for w in range(16):
+        for it in range(4):
+            if T2[w, it].max() > 0:
+                print(f"warp {w:2d} knot {it}: " + " ".join(f"{int(v - t0) if v else -1:6d}" for v in T2[w, it, :7]))
+    sys.exit(0)
 out2 = np.zeros(16 * 20 * 4, dtype=np.int64)
 lib.pb2_debug_trace2.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
 assert lib.pb2_debug_trace2(B._h, out2.ctypes.data) == 0
