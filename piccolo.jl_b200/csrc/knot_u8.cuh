@@ -30,7 +30,7 @@ namespace pb2 {
 struct U8Params {
   int m, D, x_off, dt_off, u_off, nnz_jac, max_sub, gpc, nk, zlen;
   int gw;                // warps per group: producer + (E,X) + ceil(m/2) jet warps
-  int stagger;           // cycles by which group g delays its first knot (g * stagger): de-phases the groups
+  int stagger;           // cycles by which a group with fewer knots than group 0 delays its start
   // shared-memory layout in doubles (u8_layout)
   int o_norm, o_tab, o_grp, grp_stride, zpad, o_prep, o_y, o_stage, o_mbar;
   const double* tab;     // theta_0..19 | 1/0! .. 1/19!  (40 doubles)
@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
 
   const int TG = gridDim.x * p.gpc, gg = group * gridDim.x + blockIdx.x;
   const int n_my = gg < p.nk ? (p.nk - gg + TG - 1) / TG : 0;
+  const int n_max = ((int)blockIdx.x < p.nk) ? (p.nk - (int)blockIdx.x + TG - 1) / TG : 0;   // group 0's count
   const uint32_t zbytes = (uint32_t)p.zlen * 8u;
 
   // ---- once per CTA ------------------------------------------------------------------------------
@@ -258,9 +259,10 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         if (lane <= kMaxDeg) sts_f64<0>(a_p + 8u * 256u + 8u * lane, lane <= M ? if_l * pw : 0.0);
         if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_p + 8u * 276u), "r"(M), "r"(n_sub) : "memory");
         __syncwarp();
-        if (i == 0 && p.stagger > 0) {
-          // groups that run in lockstep all leave the tensor pipe idle at the same time
-          const long long t_end = t_begin + (long long)group * p.stagger;
+        if (i == 0 && p.stagger > 0 && n_my < n_max) {
+          // a group with one knot less than its neighbours starts late: its knot then fills the
+          // tensor pipe while the others sit between two knots
+          const long long t_end = t_begin + (long long)p.stagger;
           while (clock64() < t_end) { }
         }
         if (lane == 0) mbar_arrive(mb_ready + 8 * (i & 1));
@@ -306,7 +308,8 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
       __syncwarp();
       s3 = s3 == 2 ? 0 : s3 + 1;
     }
-    if (lane == 0) bulk_wait0();
+    // the stage must outlive the bulk stores' reads of it; their writes complete with the grid
+    if (lane == 0) bulk_wait_read0();
     return;
   }
 

@@ -93,7 +93,7 @@ struct pb2_handle {
   long long* dTrace2 = nullptr;
   int n_sm = 148, gpc_default = 3, gpc_override = 0;
   bool u8_ok = false;
-  int stagger = 0;
+  int stagger = 5000;   // cycles; PB2_STAGGER overrides (0 = off)
   int pdl = 1;
   pb2::EllEntry* dEll = nullptr;
   // staging for host-pointer calls
