@@ -1,0 +1,145 @@
+# PiccoloB200.jl -- thin `ccall` shim that plugs libpiccolo_b200.so (include/piccolo_b200.h) into
+# Piccolo.jl's existing integrator extension point.
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia toolchain and DirectTrajOpt.jl
+# is not vendored in the reference, so the exact abstract-method signatures below are the ones
+# visible from the reference's call sites:
+#   evaluate!(δ, B, traj)                    src/control/integrators.jl:311, display/inspect.jl:623
+#   eval_jacobian(B, traj) / *_structure     integrators.jl:780-782, test/aqua.jl:6-9
+#   B.dim, B.x_dim, B.x_name                 integrators.jl:307-309,552
+#   integrator= kwarg                        templates/smooth_pulse_problem.jl:123,213-233
+#   register_integrator!                     src/specs/registries.jl:112,191
+# Keep it mechanical: every numeric call is one ccall; no arithmetic happens in Julia.
+module PiccoloB200
+
+using SparseArrays
+using Piccolo
+using DirectTrajOpt
+import DirectTrajOpt: AbstractIntegrator
+
+const LIB = get(ENV, "PICCOLO_B200_LIB", "libpiccolo_b200")
+
+const PB2_KET, PB2_UNITARY, PB2_DENSITY = Cint(0), Cint(1), Cint(2)
+const PB2_HOST = Cint(0)
+
+# mirrors `pb2_desc` in include/piccolo_b200.h (field order and widths must match)
+struct PB2Desc
+    kind::Int32; b::Int32; n_b::Int32; m::Int32; K::Int32; D::Int32
+    x_off::Int32; dt_off::Int32; u_off::Int32; global_dim::Int32
+    knot0::Int64; device::Int32; algorithm::Int32
+    G0::Ptr{Float64}; Gj::Ptr{Float64}
+end
+
+check(rc) = rc == 0 || error("libpiccolo_b200: " * unsafe_string(ccall((:pb2_last_error, LIB), Cstring, ())))
+
+mutable struct B200BilinearIntegrator <: AbstractIntegrator
+    handle::Ptr{Cvoid}
+    x_name::Symbol
+    u_name::Symbol
+    x_dim::Int
+    dim::Int                      # x_dim * (N - 1)            integrators.jl:309
+    nnz_jac::Int
+    nnz_hess::Int
+    ncols::Int                    # traj.dim * traj.N + traj.global_dim   integrators.jl:780-782
+    function B200BilinearIntegrator(kind, G0::Matrix{Float64}, Gj::Vector{Matrix{Float64}},
+                                    traj, x_name::Symbol, u_name::Symbol; device = 0)
+        b = size(G0, 1)
+        n_b = kind == PB2_UNITARY ? b ÷ 2 : 1
+        Gjflat = isempty(Gj) ? zeros(1) : reduce(vcat, vec.(Gj))
+        comps = traj.components
+        desc = PB2Desc(kind, b, n_b, length(Gj), traj.N, traj.dim,
+                       first(comps[x_name]) - 1, first(comps[traj.timestep]) - 1, first(comps[u_name]) - 1,
+                       traj.global_dim, 0, device, 0, pointer(G0), pointer(Gjflat))
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve G0 Gjflat check(ccall((:pb2_create, LIB), Cint, (Ref{PB2Desc}, Ref{Ptr{Cvoid}}), desc, h))
+        B = new(h[], x_name, u_name, b * n_b,
+                ccall((:pb2_dim, LIB), Int64, (Ptr{Cvoid},), h[]),
+                ccall((:pb2_nnz_jac, LIB), Int64, (Ptr{Cvoid},), h[]),
+                ccall((:pb2_nnz_hess, LIB), Int64, (Ptr{Cvoid},), h[]),
+                traj.dim * traj.N + traj.global_dim)
+        finalizer(B -> ccall((:pb2_destroy, LIB), Cvoid, (Ptr{Cvoid},), B.handle), B)
+        return B
+    end
+end
+
+# ---- generator factors: exactly what the reference's closures add up per knot --------------------
+# G(u) = G_drift + Σ_j u_j G_drives[j]                   src/quantum/systems/quantum_systems.jl:212-227
+generator_parts(sys::QuantumSystem) = (Matrix(sys.G_drift), [Matrix(G) for G in sys.G_drives])
+# compact Lindbladian factors P·(G(ad_vec H) [+ Σ iso_D(L)])·L   open_quantum_systems.jl:541-562
+function generator_parts(sys::OpenQuantumSystem)
+    𝒢d, 𝒢s, _ = Piccolo.compact_lindbladian_parts(sys)
+    return Matrix(𝒢d), [Matrix(G) for G in 𝒢s]
+end
+
+linear_drives_only(sys) = all(d -> d isa Piccolo.LinearDrive, sys.drives)   # drives.jl:93-99
+
+# ---- constructors mirroring src/control/integrators.jl:35-95 ---------------------------------------
+# Anything the C ABI cannot express (nonlinear / time-dependent drives) falls through to the
+# reference's own integrator, decided here at construction time.
+function Piccolo.BilinearIntegrator(qtraj::UnitaryTrajectory, traj::NamedTrajectory, ::Val{:b200})
+    sys = qtraj.system
+    (sys.time_dependent || !linear_drives_only(sys)) && return BilinearIntegrator(qtraj, traj.N)
+    G0, Gj = generator_parts(sys)
+    B200BilinearIntegrator(PB2_UNITARY, G0, Gj, traj, Piccolo.state_name(qtraj), Piccolo.drive_name(qtraj))
+end
+function Piccolo.BilinearIntegrator(qtraj::KetTrajectory, traj::NamedTrajectory, ::Val{:b200})
+    sys = qtraj.system
+    (sys.time_dependent || !linear_drives_only(sys)) && return BilinearIntegrator(qtraj, traj.N)
+    G0, Gj = generator_parts(sys)
+    B200BilinearIntegrator(PB2_KET, G0, Gj, traj, Piccolo.state_name(qtraj), Piccolo.drive_name(qtraj))
+end
+function Piccolo.BilinearIntegrator(qtraj::DensityTrajectory, traj::NamedTrajectory, ::Val{:b200})
+    sys = qtraj.system
+    (sys.time_dependent || !linear_drives_only(sys)) && return BilinearIntegrator(qtraj, traj.N)
+    G0, Gj = generator_parts(sys)
+    B200BilinearIntegrator(PB2_DENSITY, G0, Gj, traj, Piccolo.state_name(qtraj), Piccolo.drive_name(qtraj))
+end
+
+# ---- the AbstractIntegrator interface --------------------------------------------------------------
+function DirectTrajOpt.evaluate!(δ::AbstractVector{Float64}, B::B200BilinearIntegrator, traj::NamedTrajectory)
+    check(ccall((:pb2_residual, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint),
+                B.handle, traj.datavec, δ, PB2_HOST))
+    return nothing
+end
+
+function DirectTrajOpt.jacobian_structure(B::B200BilinearIntegrator)
+    rows = Vector{Int64}(undef, B.nnz_jac); cols = similar(rows)
+    check(ccall((:pb2_structure_jac, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), B.handle, rows, cols))
+    return collect(zip(rows, cols))          # (row, col) tuples, 1-based: test/test_utils.jl:17-30
+end
+
+function DirectTrajOpt.jacobian!(vals::AbstractVector{Float64}, B::B200BilinearIntegrator, traj::NamedTrajectory)
+    check(ccall((:pb2_jacobian, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint),
+                B.handle, traj.datavec, vals, PB2_HOST))
+    return nothing
+end
+
+function DirectTrajOpt.eval_jacobian(B::B200BilinearIntegrator, traj::NamedTrajectory)
+    rows = Vector{Int64}(undef, B.nnz_jac); cols = similar(rows); vals = Vector{Float64}(undef, B.nnz_jac)
+    check(ccall((:pb2_structure_jac, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), B.handle, rows, cols))
+    DirectTrajOpt.jacobian!(vals, B, traj)
+    return sparse(rows, cols, vals, B.dim, B.ncols)       # size pinned at integrators.jl:780-782
+end
+
+function DirectTrajOpt.hessian_structure(B::B200BilinearIntegrator)
+    rows = Vector{Int64}(undef, B.nnz_hess); cols = similar(rows)
+    check(ccall((:pb2_structure_hess, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), B.handle, rows, cols))
+    return collect(zip(rows, cols))
+end
+
+function DirectTrajOpt.hessian_of_lagrangian!(vals::AbstractVector{Float64}, B::B200BilinearIntegrator,
+                                              traj::NamedTrajectory, μ::AbstractVector{Float64})
+    check(ccall((:pb2_hess_lagrangian, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                B.handle, traj.datavec, μ, vals, PB2_HOST))
+    return nothing
+end
+
+# ---- registry hook: `integrator = "b200_bilinear"` in a ProblemSpec ---------------------------------
+# factory signature (qtraj, N; alg) -> integrator            src/specs/materialize.jl:216-222
+function __init__()
+    Piccolo.Specs.register_integrator!(:b200_bilinear,
+        Piccolo.Specs.RegistryEntry(factory = (qtraj, N; alg = nothing) ->
+            BilinearIntegrator(qtraj, NamedTrajectory(qtraj, N), Val(:b200))))
+end
+
+end # module
