@@ -312,12 +312,20 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(p, Z)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     for ptr in (pZ, pD, pV):
         lib.pb2_host_free(ptr)
+    # teardown order matters with captured NCCL work: drop the graphs, drain the device, then the
+    # handle; the process group is left to process exit (destroying a communicator that captured
+    # graphs still reference can block)
+    del g_step, g_kern
+    torch.cuda.synchronize()
     B.close()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

@@ -307,3 +307,65 @@ def test_auto_falls_back_to_jets_at_construction():
     B.close()
     with pytest.raises(pb.PB2Error):
         make(p, "dmma")
+
+
+# ---- the warp-specialised kernel of the 3-qubit unitary shape (b = 16, n_b = 8) ------------------
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 5, 6])
+def test_u8_kernel_drive_counts(m):
+    """Odd drive counts leave the last jet warp with one tile; m = 5, 6 use five warps per group."""
+    p, Z, mu = _random_problem("unitary", 16, m, 23, seed=900 + m)
+    B = make(p, "dmma")
+    d, v = B.residual_jacobian(Z)
+    assert np.abs(d - KN.residual(p, Z)).max() < 1e-11
+    assert np.abs(v - KN.jacobian_values(p, Z)).max() < 1e-10
+    assert np.array_equal(v, B.jacobian_values(Z))          # Jacobian-only call (no delta output)
+    d2 = np.empty(B.dim)
+    B.evaluate_(d2, Z)
+    assert np.abs(d2 - d).max() < 1e-13
+    B.close()
+
+
+def test_u8_kernel_substeps_nan_and_many_knots():
+    """Data-dependent Taylor sub-steps (||dt G|| up to ~40), NaN / inf poisoning confined to one knot,
+    and more knots than one wave of knot groups (several knots per group, ragged tail)."""
+    p, Z, mu = C.trajectory(3, 1300)
+    rng = np.random.default_rng(7)
+    big = rng.choice(p.K - 1, size=40, replace=False)
+    Z[p.dt_off, big] = np.geomspace(0.3, 12.0, big.size)
+    B = make(p, "dmma")
+    d, v = B.residual_jacobian(Z)
+    ref_d, ref_v = CP.residual(p, Z), CP.jacobian_values(p, Z)
+    assert np.abs(d - ref_d).max() < 1e-10
+    assert np.abs(v - ref_v).max() < 5e-9
+    small = np.setdiff1d(np.arange(p.K - 1), big)
+    D, Dr = d.reshape(p.K - 1, -1), ref_d.reshape(p.K - 1, -1)
+    V, Vr = v.reshape(p.K - 1, -1), ref_v.reshape(p.K - 1, -1)
+    assert np.abs(D[small] - Dr[small]).max() < RES_TOL and np.abs(V[small] - Vr[small]).max() < JAC_TOL
+    Z2 = Z.copy(order="F")
+    Z2[p.u_off + 1, 5] = np.nan
+    Z2[p.dt_off, 700] = np.inf
+    d2, v2 = B.residual_jacobian(Z2)
+    D2 = d2.reshape(p.K - 1, -1)
+    assert np.isnan(D2[5]).all() and np.isnan(D2[700]).all()
+    ok = np.setdiff1d(np.arange(p.K - 1), [5, 700])
+    assert np.array_equal(D2[ok], D[ok])
+    assert np.array_equal(v2.reshape(p.K - 1, -1)[ok], V[ok])
+    B.close()
+
+
+def test_u8_kernel_is_deterministic_and_matches_general_kernel(monkeypatch):
+    """Same inputs -> bit-identical outputs across launches; the general tensor-core kernel (forced
+    through PB2_NO_U8) agrees to rounding."""
+    p, Z, mu = C.trajectory(3, 300)
+    B = make(p, "dmma")
+    d, v = B.residual_jacobian(Z)
+    for _ in range(3):
+        d2, v2 = B.residual_jacobian(Z)
+        assert np.array_equal(d, d2) and np.array_equal(v, v2)
+    B.close()
+    monkeypatch.setenv("PB2_NO_U8", "1")
+    Bg = make(p, "dmma")
+    dg, vg = Bg.residual_jacobian(Z)
+    assert np.abs(dg - d).max() < 1e-13 and np.abs(vg - v).max() < 1e-12
+    Bg.close()
