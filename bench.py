@@ -46,7 +46,8 @@ def ncu_traffic(workload):
     """dram bytes per launch of the dominant kernel from the committed ncu --set full capture."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
-        return json.load(open(path)).get(workload)
+        v = json.load(open(path)).get(workload)
+        return v if isinstance(v, (int, float)) else None
     return None
 
 
