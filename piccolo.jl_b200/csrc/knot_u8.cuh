@@ -31,6 +31,8 @@ struct U8Params {
   int m, D, x_off, dt_off, u_off, nnz_jac, max_sub, gpc, nk, zlen;
   int gw;                // warps per group: producer + (E,X) + ceil(m/2) jet warps
   int stagger;           // cycles by which a group with fewer knots than group 0 delays its start
+  int stagger_g;         // additional delay of group g: g * stagger_g cycles
+  int dry;               // debug: 1 = exit after the prologue, 2 = exit immediately (launch-floor measurement)
   // shared-memory layout in doubles (u8_layout)
   int o_norm, o_tab, o_grp, grp_stride, zpad, o_prep, o_y, o_stage, o_mbar;
   const double* tab;     // theta_0..19 | 1/0! .. 1/19!  (40 doubles)
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
   // ---- once per CTA ------------------------------------------------------------------------------
   // the producer lane first arms its group's mbarriers and starts the first two slab loads, so that
   // the HBM latency of the slabs overlaps the table fill below
+  if (p.dry == 2) return;
   // programmatic dependent launch: let the next grid on the stream start its own prologue as
   // SMs drain, and do not touch trajectory / output memory before the previous grid is complete
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -173,6 +176,11 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
     mbar_init(mb_staged, ncw);
     mbar_init(mb_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // pull the first slabs towards L2 while the previous grid drains (a hint: no data is consumed
+    // before the dependency wait below)
+    for (int i = 0; i < 2 && i < n_my; ++i)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.Z + (size_t)(gg + i * TG) * p.D), "r"(zbytes)
+                   : "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int i = 0; i < 2 && i < n_my; ++i) {
       mbar_expect_tx(mb_zfull + 8 * i, zbytes);
@@ -180,14 +188,34 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
     }
     mbar_arrive(mb_free);   // the stage starts free
   }
-  for (int e = threadIdx.x; e < (m + 1) * 256; e += blockDim.x) u8_smem[e] = p.Gfrag[e];
-  for (int e = threadIdx.x; e <= m; e += blockDim.x) u8_smem[p.o_norm + e] = p.norms[e];
-  for (int e = threadIdx.x; e < 40; e += blockDim.x) u8_smem[p.o_tab + e] = p.tab[e];
+  {
+    // table fill: every global load is issued before the first shared-memory store, so the
+    // L2 latency is paid once, not once per loop trip
+    const int ncg = (m + 1) * 256, nthr = blockDim.x;
+    const double nv = (int)threadIdx.x <= m ? __ldg(p.norms + threadIdx.x) : 0.0;
+    const double tv = threadIdx.x < 40 ? __ldg(p.tab + threadIdx.x) : 0.0;
+    for (int base = 0; base < ncg; base += 8 * nthr) {   // one trip unless the CTA is very small
+      double gv[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int e = base + threadIdx.x + r * nthr;
+        gv[r] = e < ncg ? __ldg(p.Gfrag + e) : 0.0;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const int e = base + threadIdx.x + r * nthr;
+        if (e < ncg) u8_smem[e] = gv[r];
+      }
+    }
+    if ((int)threadIdx.x <= m) u8_smem[p.o_norm + threadIdx.x] = nv;
+    if (threadIdx.x < 40) u8_smem[p.o_tab + threadIdx.x] = tv;
+  }
   {
     double* ones = u8_smem + p.o_grp + group * p.grp_stride + p.o_stage + 2048 + (m + 1) * 128;
     for (int e = wg * 32 + lane; e < 128; e += 32 * gw) ones[e] = 1.0;
   }
   __syncthreads();
+  if (p.dry == 1) return;
 
   if (role == 0) {
     // =============================== producer warp ===============================================
@@ -205,7 +233,8 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         U8_STAMP(0);
         mbar_wait(mb_zfull + 8 * s3, (uint32_t)((i / 3) & 1));
         U8_STAMP(1);
-        double uj[6], nj[6];
+        // all shared-memory loads first (they are independent), then the arithmetic
+        double uj[6], nj[6], gv[6][8], acc[8];
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
           uj[j] = 0.0;
@@ -217,18 +246,26 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         }
         double dt = lds_f64<0>(a_z + 8u * p.dt_off);
         double nrm = lds_f64<0>(a_cG + 8u * p.o_norm);
-        double acc[8];
 #pragma unroll
         for (int s = 0; s < 8; ++s) acc[s] = lds_f64<0>(a_cG + 8u * (uint32_t)(s * 32 + lane));
 #pragma unroll
-        for (int j = 0; j < 6; ++j) {
+        for (int j = 0; j < 4; ++j) {
           if (j < m) {
             const uint32_t a_gj = a_cG + 8u * (uint32_t)((1 + j) * 256 + lane);
-            double gv[8];
 #pragma unroll
-            for (int s = 0; s < 8; ++s) gv[s] = lds_f64<0>(a_gj + 256u * s);
+            for (int s = 0; s < 8; ++s) gv[j][s] = lds_f64<0>(a_gj + 256u * s);
+          }
+        }
 #pragma unroll
-            for (int s = 0; s < 8; ++s) acc[s] = fma(uj[j], gv[s], acc[s]);
+        for (int j = 0; j < 6; ++j) {
+          if (j < m) {
+            if (j >= 4) {   // drives 5, 6: loaded late to bound register use
+              const uint32_t a_gj = a_cG + 8u * (uint32_t)((1 + j) * 256 + lane);
+#pragma unroll
+              for (int s = 0; s < 8; ++s) gv[j][s] = lds_f64<0>(a_gj + 256u * s);
+            }
+#pragma unroll
+            for (int s = 0; s < 8; ++s) acc[s] = fma(uj[j], gv[j][s], acc[s]);
             nrm = fma(fabs(uj[j]), nj[j], nrm);
           }
         }
@@ -259,10 +296,11 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         if (lane <= kMaxDeg) sts_f64<0>(a_p + 8u * 256u + 8u * lane, lane <= M ? if_l * pw : 0.0);
         if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_p + 8u * 276u), "r"(M), "r"(n_sub) : "memory");
         __syncwarp();
-        if (i == 0 && p.stagger > 0 && n_my < n_max) {
-          // a group with one knot less than its neighbours starts late: its knot then fills the
-          // tensor pipe while the others sit between two knots
-          const long long t_end = t_begin + (long long)p.stagger;
+        if (i == 0) {
+          // groups that run in lockstep leave the tensor pipe idle, and flood L2 with their stores,
+          // all at the same time: de-phase them.  A group with one knot less than its neighbours
+          // starts later still, so that its knot fills the pipe while the others sit between two knots.
+          const long long t_end = t_begin + (long long)group * p.stagger_g + (n_my < n_max ? (long long)p.stagger : 0);
           while (clock64() < t_end) { }
         }
         if (lane == 0) mbar_arrive(mb_ready + 8 * (i & 1));
@@ -318,7 +356,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
   if (role == 1) {
     // ---- tiles E (columns 0..7 of the propagator) and X (the 8 state columns) -------------------
     const int iE = (g == 2 * q) ? 0 : ((g == 2 * q + 1) ? 1 : -1);   // which element is the unit entry
-    const uint32_t ypub = a_y + 8u * (uint32_t)(g * 4 + q);
+    const uint32_t ypub0 = a_y + 8u * (uint32_t)(g * 4 + q);
     const uint32_t oE1 = a_stage + lane_col, oE2 = a_stage + 8u * 128u + lane_col;
     const uint32_t oD = a_stage + o_D + lane_col, oT = a_stage + o_J + 8u * (uint32_t)(m * 128) + lane_col;
     const uint32_t xl = 8u * (uint32_t)p.x_off + lane_col;
@@ -349,7 +387,9 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
           tX[i4] = cM * bX[i4];
         }
       }
-      bar_sync(xbar, nx);   // the exchange buffers are free (readers of the previous knot are done)
+      // exchange buffers alternate with the knot's parity: readers of the previous knot are never
+      // overtaken (this warp passes a knot's step barriers only together with them)
+      const uint32_t ypub = ypub0 + (uint32_t)(i & 1) * 2048u;
       U8_STAMP(2);
       {
         int kq = M - 1;
@@ -449,7 +489,16 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
       for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) t[a][i4] = 0.0;
-      bar_sync(xbar, nx);
+      if (i > 0) {
+        // switch to the other pair of exchange buffers
+        const uint32_t dy = (i & 1) ? 2048u : (uint32_t)-2048;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4)
+#pragma unroll
+            for (int ww = 0; ww < W; ++ww) yad[a][i4][ww] += dy;
+      }
       U8_STAMP(2);
       {
         // the jets start from zero: the first step is the coupling term alone
@@ -496,7 +545,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
 }
 
 // Shared-memory layout (doubles; every region 16-byte aligned).  CTA-wide: fragment tables
-// [(m+1) 256], norms.  Per group: slab x3 | prepared knot x2 | X exchange x2 | stage
+// [(m+1) 256], norms.  Per group: slab x3 | prepared knot x2 | X exchange x4 | stage
 // [E x8 (2048) | jets, d/d dt, ones ((m+2) 128) | delta (128)] | mbarriers.
 inline size_t u8_layout(U8Params& q, int gpc) {
   auto even = [](int v) { return (v + 1) & ~1; };
@@ -506,7 +555,7 @@ inline size_t u8_layout(U8Params& q, int gpc) {
   q.zpad = even(q.zlen);
   q.o_prep = 3 * q.zpad;
   q.o_y = q.o_prep + 2 * kU8Prep;
-  q.o_stage = q.o_y + 2 * 128;
+  q.o_stage = q.o_y + 4 * 128;
   q.o_mbar = q.o_stage + 2048 + (q.m + 2) * 128 + 128;
   q.grp_stride = q.o_mbar + 8;
   return sizeof(double) * ((size_t)q.o_grp + (size_t)gpc * q.grp_stride);

@@ -95,6 +95,7 @@ struct pb2_handle {
   bool u8_ok = false;
   int stagger = 5000;   // cycles; PB2_STAGGER overrides (0 = off)
   int pdl = 1;
+  int stagger_g = 0;
   pb2::EllEntry* dEll = nullptr;
   // staging for host-pointer calls
   double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
@@ -133,6 +134,8 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.zlen = p.D + p.x_off + 128;
     q.gw = 2 + (p.m + 1) / 2;
     q.stagger = h->stagger;
+    q.stagger_g = h->stagger_g;
+    if (const char* env = std::getenv("PB2_DRY")) q.dry = std::atoi(env);
     q.Gfrag = h->dGfrag; q.ell = h->dEll; q.norms = h->dNorms; q.tab = h->dTab;
     q.Z = dZ; q.delta = ddelta; q.jac = djac; q.trace = h->dTrace2;
     int maxg = std::min(pb2::kU8MaxGroups, pb2::kU8MaxThreads / (32 * q.gw));
@@ -385,6 +388,7 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     if (const char* env = std::getenv("PB2_GPC")) h->gpc_override = std::atoi(env);
     if (const char* env = std::getenv("PB2_STAGGER")) h->stagger = std::atoi(env);
     if (const char* env = std::getenv("PB2_PDL")) h->pdl = std::atoi(env);
+    if (const char* env = std::getenv("PB2_STAGGER_G")) h->stagger_g = std::atoi(env);
     h->u8_ok = h->plan.iso && d.b == 16 && d.n_b == 8 && d.m >= 1 && d.m <= 6 && !std::getenv("PB2_NO_U8");
     if (h->u8_ok)
       PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8_kernel(h->plan.W), cudaFuncAttributeMaxDynamicSharedMemorySize,

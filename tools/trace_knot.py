@@ -9,7 +9,7 @@ import piccolo_b200 as pb
 from oracle import configs as C
 
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-p, Z, _ = C.trajectory(cfg)
+p, Z, _ = C.trajectory(cfg, int(sys.argv[2]) if len(sys.argv) > 2 else None)
 B = pb.B200BilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off, dt_off=p.dt_off, u_off=p.u_off)
 for _ in range(3):
     B.residual_jacobian(Z)
@@ -36,7 +36,7 @@ if B.algorithm == "dmma" and p.b == 16 and p.n_b == 8 and not os.environ.get("PB
     for w in range(16):
         for it in range(4):
             if T2[w, it].max() > 0:
-                print(f"warp {w:2d} knot {it}: " + " ".join(f"{int(v - t0) if v else -1:6d}" for v in T2[w, it, :7]))
+                print(f"warp {w:2d} knot {it}: " + " ".join(f"{int(v - t0) if v else -1:6d}" for v in T2[w, it, :8]))
     sys.exit(0)
 out2 = np.zeros(16 * 20 * 4, dtype=np.int64)
 lib.pb2_debug_trace2.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
