@@ -169,6 +169,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout carries the JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     p, Z, _ = C.trajectory(args.config)
@@ -176,19 +179,25 @@ def run_ours(args):
     B = pb.B200BilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off,
                                   dt_off=p.dt_off, u_off=p.u_off, device=local,
                                   knot0=rank * n_eval, algorithm=args.algorithm)
-    chunk = B.dim + B.nnz_jac            # doubles this rank contributes per step
+    chunk = B.dim + B.nnz_jac            # doubles of the canonical [delta | values] arrays per rank
+    # N > 1: what crosses NVLink is the compact record per knot (the d/dx_k block is n_b copies of one
+    # b x b block); one all-gather of the records, then a local expansion into the canonical arrays
+    cs = B.compact_stride if world > 1 else 0
     # rotating buffer sets so that consecutive steps never find their lines in L2
-    set_bytes = 8 * (chunk * world + p.D * p.K)
+    set_bytes = 8 * (chunk * world + p.D * p.K + (cs * n_eval * (world + 1) if cs else 0))
     nsets = max(2, int(np.ceil(2.2 * L2_BYTES / set_bytes)))
     rng = np.random.default_rng(rank)
     zflat = Z.reshape(-1, order="F")
-    Zs, outs = [], []
+    Zs, outs, comp_loc, comp_all = [], [], [], []
     for s in range(nsets):
         zz = zflat.copy()
         if s:  # distinct data per set (tiny perturbation of the controls' low bits is enough)
             zz += 1e-9 * rng.standard_normal(zz.size)
         Zs.append(torch.from_numpy(zz).to(dev))
         outs.append(torch.empty(chunk * world, dtype=torch.float64, device=dev))
+        if cs:
+            comp_all.append(torch.empty(cs * n_eval * world, dtype=torch.float64, device=dev))
+            comp_loc.append(comp_all[-1][rank * cs * n_eval:(rank + 1) * cs * n_eval])
     # a dedicated non-default stream: the kernels, the timing events and (N > 1) the collective
     # all go on it, so the CUDA events bracket exactly the work they claim to
     stream = torch.cuda.Stream(device=dev)
@@ -197,6 +206,13 @@ def run_ours(args):
 
     def step(i, cuda_stream, collective=True):
         s = i % nsets
+        if cs:
+            B.residual_jacobian_compact_device(Zs[s], comp_loc[s], cuda_stream)
+            if collective:
+                dist.all_gather_into_tensor(comp_all[s], comp_loc[s])
+                B.expand_compact_device(comp_all[s], n_eval * world, outs[s][:B.dim * world], outs[s][B.dim * world:],
+                                        cuda_stream)
+            return
         slot = outs[s][rank * chunk:(rank + 1) * chunk]
         B.residual_jacobian_device(Zs[s], slot[:B.dim], slot[B.dim:], cuda_stream)
         if world > 1 and collective:
@@ -225,7 +241,7 @@ def run_ours(args):
     l0 = B.launch_count
     g_step = capture(True)
     g_kern = capture(False) if world > 1 else g_step
-    launches = (B.launch_count - l0) // (2 if world > 1 else 1)   # launches recorded per graph replay
+    launches = (B.launch_count - l0) - (args.steps if world > 1 else 0)   # launches recorded per replay of the step graph
     g_step.replay()          # untimed: graph upload, first-touch of every rotating set
     g_kern.replay()
     barrier()
@@ -250,6 +266,31 @@ def run_ours(args):
         kern_ms_l.append(ev[2].elapsed_time(ev[3]))
     total_ms = float(np.median(step_ms))
     kern_ms = float(np.median(kern_ms_l)) / args.steps
+
+    # ---- the Lagrangian-Hessian callback, reported separately (device-resident, same graph scheme) ----
+    hess = None
+    if world == 1:
+        dmu = torch.randn(B.dim, dtype=torch.float64, device=dev)
+        dH = [torch.empty(B.nnz_hess, dtype=torch.float64, device=dev) for _ in range(2)]
+        hsteps = max(3, min(args.steps, 50))
+        for i in range(3):
+            B.hessian_device(Zs[i % nsets], dmu, dH[i & 1], stream.cuda_stream)
+        torch.cuda.synchronize()
+        gh = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gh, stream=stream):
+            cs = torch.cuda.current_stream().cuda_stream
+            for i in range(hsteps):
+                B.hessian_device(Zs[i % nsets], dmu, dH[i & 1], cs)
+        gh.replay()
+        torch.cuda.synchronize()
+        ev[0].record()
+        gh.replay()
+        ev[1].record()
+        torch.cuda.synchronize()
+        h_ms = ev[0].elapsed_time(ev[1]) / hsteps
+        hess = {"ms_per_callback": h_ms, "evals_per_sec": n_eval / (h_ms * 1e-3), "nnz_per_knot": B.nnz_hess // max(1, n_eval),
+                "kernel": "knot_generic_kernel<2> (second-order Taylor jets in shared memory)"}
+        del gh
 
     # ---- end to end through the public host-pointer API (pinned host buffers, H2D + D2H) ----
     import ctypes
@@ -284,7 +325,7 @@ def run_ours(args):
 
     if rank == 0:
         value = n_eval * world * args.steps / (total_ms * 1e-3)
-        bytes_launch = algorithmic_bytes_per_eval(p) * n_eval
+        bytes_launch = (8 * (p.n_x + p.m + 1 + cs) if cs else algorithmic_bytes_per_eval(p)) * n_eval
         peak, peak_src = measured_peak()
         achieved = bytes_launch / (kern_ms * 1e-3) / 1e9
         workload = f"C{args.config}"
@@ -299,7 +340,9 @@ def run_ours(args):
                               "inputs and outputs resident in HBM",
                            timing=f"the {args.steps} steps are captured once as a CUDA graph and replayed; CUDA events "
                                   f"around the replay, median of {reps} replays, max over ranks",
-                           collective="one NCCL all_gather_into_tensor of [delta|vals] per step" if world > 1 else "none"),
+                           collective=("one NCCL all_gather_into_tensor of the compact per-knot records "
+                                       f"({8 * cs} B/knot instead of {8 * (p.n_x + p.nnz_jac_knot)} B), then a local expansion kernel" if cs
+                                       else "one NCCL all_gather_into_tensor of [delta|vals] per step") if world > 1 else "none"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(workload),
                          "kernel": f"knot resjac ({B.algorithm})", "kernel_ms": kern_ms,
@@ -308,6 +351,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": 8 * p.D * p.K, "d2h_bytes_per_step": 8 * (B.dim + B.nnz_jac),
                     "steps": e2e_steps,
                     "note": "pb2_residual_jacobian with pinned host buffers; per rank its own shard"},
+            "hessian": hess,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }

@@ -18,6 +18,7 @@ SYMBOLS = [
     "pb2_dim", "pb2_nnz_jac", "pb2_nnz_hess", "pb2_algorithm", "pb2_structure_jac",
     "pb2_structure_hess", "pb2_residual", "pb2_jacobian", "pb2_residual_jacobian",
     "pb2_hess_lagrangian", "pb2_residual_jacobian_async", "pb2_hess_lagrangian_async",
+    "pb2_compact_stride", "pb2_residual_jacobian_compact_async", "pb2_expand_compact_async",
     "pb2_stream", "pb2_sync", "pb2_host_alloc", "pb2_host_free", "pb2_launch_count",
 ]
 
@@ -77,6 +78,10 @@ def load_library():
     L.pb2_residual_jacobian_async.argtypes = [H, vp, vp, vp, vp]
     L.pb2_hess_lagrangian_async.argtypes = [H, vp, vp, vp, vp]
     L.pb2_sync.argtypes = [H]
+    L.pb2_compact_stride.argtypes = [H]
+    L.pb2_compact_stride.restype = ctypes.c_int64
+    L.pb2_residual_jacobian_compact_async.argtypes = [H, vp, vp, vp]
+    L.pb2_expand_compact_async.argtypes = [H, vp, ctypes.c_int64, vp, vp, vp]
     L.pb2_stream.argtypes = [H]
     L.pb2_stream.restype = ctypes.c_void_p
     L.pb2_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_int64]

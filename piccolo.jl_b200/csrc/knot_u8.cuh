@@ -32,6 +32,8 @@ struct U8Params {
   int gw;                // warps per group: producer + (E,X) + ceil(m/2) jet warps
   int stagger;           // cycles by which a group with fewer knots than group 0 delays its start
   int stagger_g;         // additional delay of group g: g * stagger_g cycles
+  int compact;           // 1: write [E once | jets, d/d dt, ones | delta] records of cstride doubles to `jac`
+  int cstride;
   int dry;               // debug: 1 = exit after the prologue, 2 = exit immediately (launch-floor measurement)
   // shared-memory layout in doubles (u8_layout)
   int o_norm, o_tab, o_grp, grp_stride, zpad, o_prep, o_y, o_stage, o_mbar;
@@ -313,18 +315,27 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         U8_STAMP(3);
         mbar_wait(mb_staged, (uint32_t)((i - 1) & 1));
         U8_STAMP(4);
-        double2 v[4];
+        if (!p.compact) {
+          double2 v[4];
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) v[jj] = lds_f64x2<0>(a_stage + 16u * (uint32_t)(lane + 32 * jj));
+          for (int jj = 0; jj < 4; ++jj) v[jj] = lds_f64x2<0>(a_stage + 16u * (uint32_t)(lane + 32 * jj));
 #pragma unroll
-        for (int c = 1; c < 8; ++c)
+          for (int c = 1; c < 8; ++c)
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) sts_f64x2<0>(a_stage + 2048u * c + 16u * (uint32_t)(lane + 32 * jj), v[jj]);
+            for (int jj = 0; jj < 4; ++jj) sts_f64x2<0>(a_stage + 2048u * c + 16u * (uint32_t)(lane + 32 * jj), v[jj]);
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          bulk_s2g(p.jac + (size_t)kprev * p.nnz_jac, a_stage, (uint32_t)p.nnz_jac * 8u);
-          if (p.delta) bulk_s2g(p.delta + (size_t)kprev * 128, a_stage + o_D, 1024u);
+          if (p.compact) {
+            // record = [E (256) | jets, d/d dt, ones | delta]: what crosses NVLink in a sharded run
+            double* rec = p.jac + (size_t)kprev * p.cstride;
+            bulk_s2g(rec, a_stage, 2048u);
+            bulk_s2g(rec + 256, a_stage + o_J, (uint32_t)(m + 3) * 1024u);
+          } else {
+            bulk_s2g(p.jac + (size_t)kprev * p.nnz_jac, a_stage, (uint32_t)p.nnz_jac * 8u);
+            if (p.delta) bulk_s2g(p.delta + (size_t)kprev * 128, a_stage + o_D, 1024u);
+          }
           bulk_commit();
         }
         U8_STAMP(5);
@@ -423,7 +434,8 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
       double dT[2][2];
       u8_mma(dT, tX, A);
       double xn[4];
-      if (p.delta) {
+      const bool want_delta = p.delta != nullptr || p.compact;
+      if (want_delta) {
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) xn[i4] = lds_f64<0>(a_z + 8u * p.D + xl + U8_OFF(i4));
       }
@@ -433,7 +445,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
       // -E = -[[P, -Q], [Q, P]]: own column g, mirrored column g + 8
       sts_f64<0>(oE1, -tE[0]);   sts_f64<8>(oE1, -tE[1]);   sts_f64<64>(oE1, -tE[2]);  sts_f64<72>(oE1, -tE[3]);
       sts_f64<64>(oE2, -tE[0]);  sts_f64<72>(oE2, -tE[1]);  sts_f64<0>(oE2, tE[2]);    sts_f64<8>(oE2, tE[3]);
-      if (p.delta) {
+      if (want_delta) {
         sts_f64<0>(oD, xn[0] - tX[0]);   sts_f64<8>(oD, xn[1] - tX[1]);
         sts_f64<64>(oD, xn[2] - tX[2]);  sts_f64<72>(oD, xn[3] - tX[3]);
       }
@@ -559,6 +571,26 @@ inline size_t u8_layout(U8Params& q, int gpc) {
   q.o_mbar = q.o_stage + 2048 + (q.m + 2) * 128 + 128;
   q.grp_stride = q.o_mbar + 8;
   return sizeof(double) * ((size_t)q.o_grp + (size_t)gpc * q.grp_stride);
+}
+
+// Compact records -> canonical arrays: [E | J | delta] per knot becomes n_b copies of E, J, and delta.
+// Pure data movement (HBM-bound); one CTA per knot, grid-stride.
+__global__ void __launch_bounds__(256) expand_compact_kernel(const double* __restrict__ comp, long long n_knots,
+                                                             int cstride, int bb, int n_b, int nJ, int n_x,
+                                                             int nnz_jac, double* __restrict__ delta,
+                                                             double* __restrict__ jac) {
+  for (long long r = blockIdx.x; r < n_knots; r += gridDim.x) {
+    const double* src = comp + r * cstride;
+    double* out = jac + r * nnz_jac;
+    for (int e = threadIdx.x; e < bb; e += blockDim.x) {
+      const double v = src[e];
+      for (int c = 0; c < n_b; ++c) out[(size_t)c * bb + e] = v;
+    }
+    out += (size_t)n_b * bb;
+    for (int e = threadIdx.x; e < nJ; e += blockDim.x) out[e] = src[bb + e];
+    if (delta)
+      for (int e = threadIdx.x; e < n_x; e += blockDim.x) delta[r * n_x + e] = src[bb + nJ + e];
+  }
 }
 
 using U8Kernel = void (*)(U8Params);

@@ -120,7 +120,7 @@ pb2::KnotParams make_params(const pb2_handle* h) {
   return p;
 }
 
-int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st) {
+int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, bool compact = false) {
   if (h->nk() <= 0) return PB2_OK;
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.delta = ddelta; p.jac = djac;
@@ -135,6 +135,8 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.gw = 2 + (p.m + 1) / 2;
     q.stagger = h->stagger;
     q.stagger_g = h->stagger_g;
+    q.compact = compact ? 1 : 0;
+    q.cstride = 256 + (p.m + 3) * 128;
     if (const char* env = std::getenv("PB2_DRY")) q.dry = std::atoi(env);
     q.Gfrag = h->dGfrag; q.ell = h->dEll; q.norms = h->dNorms; q.tab = h->dTab;
     q.Z = dZ; q.delta = ddelta; q.jac = djac; q.trace = h->dTrace2;
@@ -158,6 +160,8 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     cudaError_t e = cudaLaunchKernelEx(&cfg, pb2::u8_kernel(pl.W), q);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("u8 resjac launch: ") + cudaGetErrorString(e));
+  } else if (compact) {
+    return fail(PB2_EINVAL, "compact records are only produced by the 3-qubit unitary kernel with aligned pointers");
   } else if (h->alg == PB2_ALG_DMMA) {
     // residual-only calls carry just the state columns; anything with a Jacobian carries the
     // propagator columns and one jet per drive as well
@@ -515,6 +519,37 @@ int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu
   if (!dZ || !dmu || !dvals) return fail(PB2_EINVAL, "pb2_hess_lagrangian_async: null argument");
   PB2_CUDA(cudaSetDevice(h->d.device));
   return launch_hess(h, dZ, dmu, dvals, (cudaStream_t)stream);
+}
+
+int64_t pb2_compact_stride(const pb2_handle* h) {
+  if (!h || !(h->alg == PB2_ALG_DMMA && h->u8_ok) || (h->d.D % 2) || (h->d.x_off % 2)) return 0;
+  return 256 + (int64_t)(h->d.m + 3) * 128;
+}
+
+int pb2_residual_jacobian_compact_async(pb2_handle* h, const double* dZ, double* dcompact, void* stream) {
+  if (check(h)) return PB2_EINVAL;
+  if (!dZ || !dcompact) return fail(PB2_EINVAL, "pb2_residual_jacobian_compact_async: null argument");
+  if (pb2_compact_stride(h) == 0) return fail(PB2_EINVAL, "pb2_residual_jacobian_compact_async: unsupported for this handle");
+  PB2_CUDA(cudaSetDevice(h->d.device));
+  return launch_resjac(h, dZ, nullptr, dcompact, (cudaStream_t)stream, true);
+}
+
+int pb2_expand_compact_async(pb2_handle* h, const double* dcompact, int64_t n_knots, double* ddelta, double* dvals,
+                             void* stream) {
+  if (check(h)) return PB2_EINVAL;
+  if (!dcompact || !dvals || n_knots < 0) return fail(PB2_EINVAL, "pb2_expand_compact_async: bad argument");
+  const int64_t cs = pb2_compact_stride(h);
+  if (cs == 0) return fail(PB2_EINVAL, "pb2_expand_compact_async: unsupported for this handle");
+  if (n_knots == 0) return PB2_OK;
+  PB2_CUDA(cudaSetDevice(h->d.device));
+  const int bb = h->d.b * h->d.b, n_x = h->n_x();
+  const int blocks = (int)std::min<int64_t>(n_knots, (int64_t)h->n_sm * 8);
+  pb2::expand_compact_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dcompact, n_knots, (int)cs, bb, h->d.n_b,
+                                                                     (h->d.m + 2) * n_x, n_x, h->nnz_jac_knot(),
+                                                                     ddelta, dvals);
+  PB2_CUDA(cudaGetLastError());
+  h->launches++;
+  return PB2_OK;
 }
 
 void* pb2_stream(const pb2_handle* h) { return h ? (void*)h->stream : nullptr; }

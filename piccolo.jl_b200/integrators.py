@@ -222,6 +222,19 @@ class B200BilinearIntegrator:
         capi.check(self._lib.pb2_hess_lagrangian_async(self._h, _as_ptr(dZ), _as_ptr(dmu),
                                                        _as_ptr(dvals), _as_ptr(stream)))
 
+    # -- compact records for sharded runs (see include/piccolo_b200.h) ------------------------
+    @property
+    def compact_stride(self):
+        return int(self._lib.pb2_compact_stride(self._h))
+
+    def residual_jacobian_compact_device(self, dZ, dcompact, stream=None):
+        capi.check(self._lib.pb2_residual_jacobian_compact_async(self._h, _as_ptr(dZ), _as_ptr(dcompact),
+                                                                 _as_ptr(stream)))
+
+    def expand_compact_device(self, dcompact, n_knots, ddelta, dvals, stream=None):
+        capi.check(self._lib.pb2_expand_compact_async(self._h, _as_ptr(dcompact), int(n_knots), _as_ptr(ddelta),
+                                                      _as_ptr(dvals), _as_ptr(stream)))
+
     def sync(self):
         capi.check(self._lib.pb2_sync(self._h))
 

@@ -56,6 +56,11 @@ class ShardedBilinearIntegrator:
         self.gather = torch.zeros(max(1, self.chunk * world), dtype=torch.float64,
                                   device=self.tensor_device)
         self.zslab = torch.zeros(D * (self.n_local + 1), dtype=torch.float64, device=self.tensor_device)
+        # compact records (include/piccolo_b200.h): when the local evaluator offers them, the records
+        # are what crosses NVLink and the canonical arrays are rebuilt locally after the gather
+        self.cs = int(getattr(self.local, "compact_stride", 0)) if str(self.tensor_device).startswith("cuda") else 0
+        if self.cs:
+            self.comp = torch.zeros(max(1, self.cs * self.per * world), dtype=torch.float64, device=self.tensor_device)
 
     # views into the gather buffer ---------------------------------------------------------
     def _slot(self, r):
@@ -80,7 +85,11 @@ class ShardedBilinearIntegrator:
         if self.n_local > 0:
             if self.zslab.is_cuda:
                 st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-                self.local.residual_jacobian_device(self.zslab, self.my_delta(), self.my_vals(), st)
+                if self.cs:
+                    mine = self.comp[self.rank * self.cs * self.per:(self.rank + 1) * self.cs * self.per]
+                    self.local.residual_jacobian_compact_device(self.zslab, mine, st)
+                else:
+                    self.local.residual_jacobian_device(self.zslab, self.my_delta(), self.my_vals(), st)
             else:  # injected CPU stand-in (tests only)
                 d, v = self.local.residual_jacobian(self.zslab.numpy().reshape(self.n_local + 1, self.D).T)
                 self.my_delta()[:d.size] = torch.from_numpy(d)
@@ -88,6 +97,17 @@ class ShardedBilinearIntegrator:
 
     def all_gather(self):
         """One collective per callback: every rank ends with every rank's [delta | vals] slot."""
+        if self.cs:
+            torch = self.torch
+            mine = self.comp[self.rank * self.cs * self.per:(self.rank + 1) * self.cs * self.per]
+            if self.world > 1:
+                torch.distributed.all_gather_into_tensor(self.comp, mine, group=self.group)
+            st = torch.cuda.current_stream().cuda_stream
+            for r in range(self.world):       # every rank slot holds `per` records (the last may be ragged)
+                slot = self._slot(r)
+                self.local.expand_compact_device(self.comp[r * self.cs * self.per:], self.per,
+                                                 slot[:self.per * self.n_x], slot[self.per * self.n_x:], st)
+            return self.gather
         if self.world > 1:
             self.torch.distributed.all_gather_into_tensor(self.gather, self._slot(self.rank).clone()
                                                           if not self.gather.is_cuda else self._slot(self.rank),

@@ -369,3 +369,39 @@ def test_u8_kernel_is_deterministic_and_matches_general_kernel(monkeypatch):
     dg, vg = Bg.residual_jacobian(Z)
     assert np.abs(dg - d).max() < 1e-13 and np.abs(vg - v).max() < 1e-12
     Bg.close()
+
+
+def test_compact_records_expand_to_canonical_arrays():
+    """Sharded runs move compact per-knot records [E | jets, d/d dt, ones | delta] and expand them
+    locally: the result must be bit-identical to the directly written canonical arrays."""
+    import torch
+    p, Z, mu = C.trajectory(3, 333)
+    B = make(p, "dmma")
+    cs = B.compact_stride
+    assert cs == 256 + (p.m + 3) * 128
+    d, v = B.residual_jacobian(Z)
+    dZ = torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda()
+    n = p.K - 1
+    comp = torch.zeros(cs * n, dtype=torch.float64, device="cuda")
+    dd = torch.zeros(B.dim, dtype=torch.float64, device="cuda")
+    dv = torch.zeros(B.nnz_jac, dtype=torch.float64, device="cuda")
+    B.residual_jacobian_compact_device(dZ, comp, None)
+    B.expand_compact_device(comp, n, dd, dv, None)
+    torch.cuda.synchronize()
+    assert np.array_equal(dd.cpu().numpy(), d) and np.array_equal(dv.cpu().numpy(), v)
+    # records of two "ranks" concatenated expand like one long trajectory
+    comp2 = torch.cat([comp, comp])
+    dd2 = torch.zeros(2 * B.dim, dtype=torch.float64, device="cuda")
+    dv2 = torch.zeros(2 * B.nnz_jac, dtype=torch.float64, device="cuda")
+    B.expand_compact_device(comp2, 2 * n, dd2, dv2, None)
+    torch.cuda.synchronize()
+    assert np.array_equal(dv2.cpu().numpy(), np.concatenate([v, v]))
+    assert np.array_equal(dd2.cpu().numpy(), np.concatenate([d, d]))
+    B.close()
+    # shapes outside the 3-qubit unitary kernel do not offer the compact form
+    p2, Z2, _ = C.trajectory(2, 20)
+    B2 = make(p2)
+    assert B2.compact_stride == 0
+    with pytest.raises(pb.PB2Error):
+        B2.residual_jacobian_compact_device(dZ, comp, None)
+    B2.close()
