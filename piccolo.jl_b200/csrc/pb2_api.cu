@@ -20,6 +20,7 @@
 #include "knot_generic.cuh"
 #include "knot_dmma.cuh"
 #include "knot_u8.cuh"
+#include "knot_u8h.cuh"
 
 namespace {
 
@@ -93,6 +94,7 @@ struct pb2_handle {
   long long* dTrace2 = nullptr;
   int n_sm = 148, gpc_default = 3, gpc_override = 0;
   bool u8_ok = false;
+  bool u8h_ok = false;
   int stagger = 5000;   // cycles; PB2_STAGGER overrides (0 = off)
   int pdl = 1;
   int stagger_g = 0;
@@ -206,6 +208,24 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
   if (h->nk() <= 0) return PB2_OK;
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.mu = dmu; p.hess = dhess;
+  if (h->u8h_ok && ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)dmu % 16 == 0) && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
+    // 3-qubit unitary shape, anti-symmetric generators: tensor-core Hessian (forward + adjoint jets)
+    pb2::U8hParams q{};
+    q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
+    q.nnz_hess = p.nnz_hess; q.max_sub = 4096; q.nk = (int)h->nk();
+    q.zlen = p.D + p.x_off + 128;
+    q.ntiles = 2 + 2 * p.m + p.m * (p.m + 1) / 2;
+    q.ncw = (q.ntiles + 1) / 2;
+    q.Gfrag = h->dGfrag; q.ell = h->dEll; q.norms = h->dNorms; q.tab = h->dTab;
+    q.Z = dZ; q.mu = dmu; q.hess = dhess;
+    const size_t smem = pb2::u8h_layout(q);
+    if (smem > kSmemLimit) return fail(PB2_EINVAL, "u8h hessian: knot column too large for the shared-memory staging");
+    const int blocks = std::min(h->n_sm, q.nk);
+    pb2::u8h_kernel(h->plan.W)<<<blocks, 32 * (1 + q.ncw), smem, st>>>(q);
+    PB2_CUDA(cudaGetLastError());
+    h->launches++;
+    return PB2_OK;
+  }
   {
     // the Lagrangian Hessian always runs the jet kernel (second-order jets)
     const LaunchCfg& c = h->cfg2;
@@ -396,6 +416,19 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     h->u8_ok = h->plan.iso && d.b == 16 && d.n_b == 8 && d.m >= 1 && d.m <= 6 && !std::getenv("PB2_NO_U8");
     if (h->u8_ok)
       PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8_kernel(h->plan.W), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemLimit));
+    // the tensor-core Hessian additionally uses E^T = exp(-dt G): every generator anti-symmetric
+    // (true for the isomorphism of any Hermitian Hamiltonian, isomorphisms.jl:350,359)
+    bool antisym = true;
+    for (int mat = 0; mat <= d.m && antisym; ++mat) {
+      const double* A = mat == 0 ? h->G0.data() : h->Gj.data() + (size_t)(mat - 1) * bb;
+      for (int i = 0; i < d.b && antisym; ++i)
+        for (int j = 0; j <= i; ++j)
+          if (A[i + (size_t)j * d.b] != -A[j + (size_t)i * d.b]) { antisym = false; break; }
+    }
+    h->u8h_ok = h->u8_ok && antisym && d.m <= 4 && !std::getenv("PB2_NO_U8H");
+    if (h->u8h_ok)
+      PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8h_kernel(h->plan.W), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemLimit));
 #ifdef PB2_TRACE
     PB2_CUDA_H(cudaMalloc(&h->dTrace, 8 * 16 * 8 * sizeof(long long)));

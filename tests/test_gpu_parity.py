@@ -405,3 +405,44 @@ def test_compact_records_expand_to_canonical_arrays():
     with pytest.raises(pb.PB2Error):
         B2.residual_jacobian_compact_device(dZ, comp, None)
     B2.close()
+
+
+# ---- tensor-core Lagrangian Hessian of the 3-qubit unitary shape ---------------------------------------
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4])
+def test_u8_hessian_kernel_drive_counts(m):
+    p, Z, mu = _random_problem("unitary", 16, m, 19, seed=700 + m)
+    B = make(p, "dmma")
+    h = B.hessian_values(Z, mu)
+    ho = KN.hessian_values(p, Z, mu)
+    assert np.abs(h - ho).max() < HESS_RTOL * max(1.0, np.abs(ho).max())
+    B.close()
+
+
+def test_u8_hessian_kernel_substeps_many_knots_and_general_kernel(monkeypatch):
+    """Sub-steps (||dt G|| up to ~40), several knots per CTA, NaN confinement, and agreement with
+    the shared-memory jet kernel (forced through PB2_NO_U8H)."""
+    p, Z, mu = C.trajectory(3, 500)
+    rng = np.random.default_rng(11)
+    big = rng.choice(p.K - 1, size=25, replace=False)
+    Z[p.dt_off, big] = np.geomspace(0.3, 12.0, big.size)
+    B = make(p, "dmma")
+    h = B.hessian_values(Z, mu)
+    ref = CP.hessian_values(p, Z, mu)
+    H, R = h.reshape(p.K - 1, -1), ref.reshape(p.K - 1, -1)
+    small = np.setdiff1d(np.arange(p.K - 1), big)
+    assert np.abs(H[small] - R[small]).max() < HESS_RTOL * np.abs(R[small]).max()
+    assert np.abs(H[big] - R[big]).max() < 1e-7 * np.abs(R[big]).max()
+    assert np.array_equal(h, B.hessian_values(Z, mu))           # deterministic
+    Z2 = Z.copy(order="F")
+    Z2[p.u_off, 7] = np.nan
+    H2 = B.hessian_values(Z2, mu).reshape(p.K - 1, -1)
+    assert np.isnan(H2[7]).any()        # the poisoned knot shows it (degree-1 jets never touch G(u))
+    ok = np.setdiff1d(np.arange(p.K - 1), [7])
+    assert np.array_equal(H2[ok], H[ok])   # ... and only that knot
+    B.close()
+    monkeypatch.setenv("PB2_NO_U8H", "1")
+    Bg = make(p, "dmma")
+    hg = Bg.hessian_values(Z, mu)
+    assert np.abs(hg.reshape(p.K - 1, -1)[small] - H[small]).max() < 1e-10 * np.abs(H[small]).max()
+    Bg.close()
