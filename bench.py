@@ -277,9 +277,9 @@ def run_ours(args):
         torch.cuda.synchronize()
         gh = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gh, stream=stream):
-            cs = torch.cuda.current_stream().cuda_stream
+            hs = torch.cuda.current_stream().cuda_stream
             for i in range(hsteps):
-                B.hessian_device(Zs[i % nsets], dmu, dH[i & 1], cs)
+                B.hessian_device(Zs[i % nsets], dmu, dH[i & 1], hs)
         gh.replay()
         torch.cuda.synchronize()
         ev[0].record()

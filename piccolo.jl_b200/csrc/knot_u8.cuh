@@ -37,10 +37,8 @@ struct U8Params {
   int dry;               // debug: 1 = exit after the prologue, 2 = exit immediately (launch-floor measurement)
   // shared-memory layout in doubles (u8_layout)
   int o_norm, o_tab, o_grp, grp_stride, zpad, o_prep, o_y, o_stage, o_mbar;
-  const double* tab;     // theta_0..19 | 1/0! .. 1/19!  (40 doubles)
-  const double* Gfrag;   // (m+1) * 256 doubles, B-fragment order
+  const double* tables;  // [G fragments (m+1) 256 | norms (padded even) | theta_0..19 | 1/0! .. 1/19!], smem order
   const EllEntry* ell;   // (m+1) * 16 * W   (drive m = all-zero dummy)
-  const double* norms;   // m+1
   const double* Z;
   double* delta;         // may be null
   double* jac;
@@ -171,6 +169,15 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
   // programmatic dependent launch: let the next grid on the stream start its own prologue as
   // SMs drain, and do not touch trajectory / output memory before the previous grid is complete
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const uint32_t mb_tab = a_cG + 8u * (uint32_t)(p.o_tab + 40);
+  if (threadIdx.x == 0) {
+    // the handle's constant tables (G fragments, norms, theta / factorial tables: contiguous in HBM
+    // in shared-memory order) arrive by ONE bulk copy; only the producer warps ever wait for it
+    mbar_init(mb_tab, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(mb_tab, 8u * (uint32_t)(p.o_tab + 40));
+    bulk_g2s(a_cG, p.tables, 8u * (uint32_t)(p.o_tab + 40), mb_tab);
+  }
   if (role == 0 && lane == 0) {
     for (int i = 0; i < 3; ++i) mbar_init(mb_zfull + 8 * i, 1);
     mbar_init(mb_ready, 1);
@@ -178,39 +185,6 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
     mbar_init(mb_staged, ncw);
     mbar_init(mb_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // pull the first slabs towards L2 while the previous grid drains (a hint: no data is consumed
-    // before the dependency wait below)
-    for (int i = 0; i < 2 && i < n_my; ++i)
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.Z + (size_t)(gg + i * TG) * p.D), "r"(zbytes)
-                   : "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int i = 0; i < 2 && i < n_my; ++i) {
-      mbar_expect_tx(mb_zfull + 8 * i, zbytes);
-      bulk_g2s(a_grp + 8u * (uint32_t)(i * p.zpad), p.Z + (size_t)(gg + i * TG) * p.D, zbytes, mb_zfull + 8 * i);
-    }
-    mbar_arrive(mb_free);   // the stage starts free
-  }
-  {
-    // table fill: every global load is issued before the first shared-memory store, so the
-    // L2 latency is paid once, not once per loop trip
-    const int ncg = (m + 1) * 256, nthr = blockDim.x;
-    const double nv = (int)threadIdx.x <= m ? __ldg(p.norms + threadIdx.x) : 0.0;
-    const double tv = threadIdx.x < 40 ? __ldg(p.tab + threadIdx.x) : 0.0;
-    for (int base = 0; base < ncg; base += 8 * nthr) {   // one trip unless the CTA is very small
-      double gv[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int e = base + threadIdx.x + r * nthr;
-        gv[r] = e < ncg ? __ldg(p.Gfrag + e) : 0.0;
-      }
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int e = base + threadIdx.x + r * nthr;
-        if (e < ncg) u8_smem[e] = gv[r];
-      }
-    }
-    if ((int)threadIdx.x <= m) u8_smem[p.o_norm + threadIdx.x] = nv;
-    if (threadIdx.x < 40) u8_smem[p.o_tab + threadIdx.x] = tv;
   }
   {
     double* ones = u8_smem + p.o_grp + group * p.grp_stride + p.o_stage + 2048 + (m + 1) * 128;
@@ -221,9 +195,23 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
 
   if (role == 0) {
     // =============================== producer warp ===============================================
-    const double th_l = u8_smem[p.o_tab + (lane <= kMaxDeg ? lane : kMaxDeg)];
-    const double if_l = u8_smem[p.o_tab + 20 + (lane <= kMaxDeg ? lane : kMaxDeg)];
-    const double th_max = u8_smem[p.o_tab + kMaxDeg];
+    if (lane == 0) {
+      // pull the first slabs towards L2 while the previous grid drains (a hint: no data is consumed
+      // before the dependency wait), then wait for the previous grid and start the slab ring
+      for (int i = 0; i < 2 && i < n_my; ++i)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.Z + (size_t)(gg + i * TG) * p.D), "r"(zbytes)
+                     : "memory");
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      for (int i = 0; i < 2 && i < n_my; ++i) {
+        mbar_expect_tx(mb_zfull + 8 * i, zbytes);
+        bulk_g2s(a_grp + 8u * (uint32_t)(i * p.zpad), p.Z + (size_t)(gg + i * TG) * p.D, zbytes, mb_zfull + 8 * i);
+      }
+      mbar_arrive(mb_free);   // the stage starts free
+    }
+    mbar_wait(mb_tab, 0);
+    const double th_l = lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_tab + (lane <= kMaxDeg ? lane : kMaxDeg)));
+    const double if_l = lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_tab + 20 + (lane <= kMaxDeg ? lane : kMaxDeg)));
+    const double th_max = lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_tab + kMaxDeg));
     const long long t_begin = clock64();
     int s3 = 0;
     for (int i = 0; i <= n_my; ++i) {
@@ -563,7 +551,7 @@ inline size_t u8_layout(U8Params& q, int gpc) {
   auto even = [](int v) { return (v + 1) & ~1; };
   q.o_norm = (q.m + 1) * 256;
   q.o_tab = q.o_norm + even(q.m + 1);
-  q.o_grp = q.o_tab + 40;
+  q.o_grp = q.o_tab + 40 + 2;   // + the tables' mbarrier
   q.zpad = even(q.zlen);
   q.o_prep = 3 * q.zpad;
   q.o_y = q.o_prep + 2 * kU8Prep;

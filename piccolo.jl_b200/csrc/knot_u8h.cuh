@@ -31,10 +31,8 @@ struct U8hParams {
   int ntiles, ncw;       // tiles per knot, compute warps (= ceil(ntiles / 2))
   // shared-memory layout in doubles (u8h_layout)
   int o_norm, o_tab, o_slab, zpad, o_prep, o_xch, o_stage, o_mbar;
-  const double* tab;     // theta_0..19 | 1/0! .. 1/19!
-  const double* Gfrag;   // (m+1) * 256 doubles, B-fragment order
+  const double* tables;  // [G fragments (m+1) 256 | norms (padded even) | theta | 1/k!], smem order
   const EllEntry* ell;   // (m+1) * 16 * W
-  const double* norms;
   const double* Z;
   const double* mu;
   double* hess;
@@ -130,13 +128,18 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
   const int n_my = (int)blockIdx.x < p.nk ? (p.nk - (int)blockIdx.x + stride - 1) / stride : 0;
 
   // ---- once per CTA ------------------------------------------------------------------------------
-  if (wcta == 0 && lane == 0) {
+  const uint32_t mb_tab = a_cG + 8u * (uint32_t)(p.o_tab + 40);
+  if (threadIdx.x == 0) {
+    mbar_init(mb_tab, 1);
     for (int i = 0; i < 3; ++i) mbar_init(mb_zfull + 8 * i, 1);
     mbar_init(mb_ready, 1);
     mbar_init(mb_ready + 8, 1);
     mbar_init(mb_staged, ncw);
     mbar_init(mb_free, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // constant tables (G fragments, norms, theta / factorial tables) by one bulk copy
+    mbar_expect_tx(mb_tab, 8u * (uint32_t)(p.o_tab + 40));
+    bulk_g2s(a_cG, p.tables, 8u * (uint32_t)(p.o_tab + 40), mb_tab);
     for (int i = 0; i < 2 && i < n_my; ++i) {
       const size_t k = (size_t)blockIdx.x + (size_t)i * stride;
       mbar_expect_tx(mb_zfull + 8 * i, zbytes + 1024u);
@@ -145,33 +148,14 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
     }
     mbar_arrive(mb_free);   // the stage starts free
   }
-  {
-    const int ncg = (m + 1) * 256, nt = blockDim.x;
-    const double nv = (int)threadIdx.x <= m ? __ldg(p.norms + threadIdx.x) : 0.0;
-    const double tv = threadIdx.x < 40 ? __ldg(p.tab + threadIdx.x) : 0.0;
-    for (int b0 = 0; b0 < ncg; b0 += 8 * nt) {
-      double gv[8];
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int e = b0 + threadIdx.x + r * nt;
-        gv[r] = e < ncg ? __ldg(p.Gfrag + e) : 0.0;
-      }
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        const int e = b0 + threadIdx.x + r * nt;
-        if (e < ncg) u8_smem[e] = gv[r];
-      }
-    }
-    if ((int)threadIdx.x <= m) u8_smem[p.o_norm + threadIdx.x] = nv;
-    if (threadIdx.x < 40) u8_smem[p.o_tab + threadIdx.x] = tv;
-  }
   __syncthreads();
 
   if (wcta == 0) {
     // =============================== producer warp ===============================================
-    const double th_l = u8_smem[p.o_tab + (lane <= kMaxDeg ? lane : kMaxDeg)];
-    const double if_l = u8_smem[p.o_tab + 20 + (lane <= kMaxDeg ? lane : kMaxDeg)];
-    const double th_max = u8_smem[p.o_tab + kMaxDeg];
+    mbar_wait(mb_tab, 0);
+    const double th_l = lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_tab + (lane <= kMaxDeg ? lane : kMaxDeg)));
+    const double if_l = lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_tab + 20 + (lane <= kMaxDeg ? lane : kMaxDeg)));
+    const double th_max = lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_tab + kMaxDeg));
     int s3 = 0;
     for (int i = 0; i <= n_my; ++i) {
       if (i < n_my) {
@@ -436,7 +420,7 @@ inline size_t u8h_layout(U8hParams& q) {
   auto even = [](int v) { return (v + 1) & ~1; };
   q.o_norm = (q.m + 1) * 256;
   q.o_tab = q.o_norm + even(q.m + 1);
-  q.o_slab = q.o_tab + 40;
+  q.o_slab = q.o_tab + 40 + 2;   // + the tables' mbarrier
   q.zpad = even(q.zlen);
   q.o_prep = q.o_slab + 3 * (q.zpad + 128);
   q.o_xch = q.o_prep + 2 * kU8Prep;

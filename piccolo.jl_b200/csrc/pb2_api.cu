@@ -90,6 +90,7 @@ struct pb2_handle {
   double* dGfrag = nullptr;
   double* dNorms = nullptr;
   double* dTab = nullptr;
+  double* dTables = nullptr;   // [gfrag | norms (even) | theta | 1/k!] contiguous, the u8 kernels' smem order
   long long* dTrace = nullptr;
   long long* dTrace2 = nullptr;
   int n_sm = 148, gpc_default = 3, gpc_override = 0;
@@ -140,7 +141,7 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.compact = compact ? 1 : 0;
     q.cstride = 256 + (p.m + 3) * 128;
     if (const char* env = std::getenv("PB2_DRY")) q.dry = std::atoi(env);
-    q.Gfrag = h->dGfrag; q.ell = h->dEll; q.norms = h->dNorms; q.tab = h->dTab;
+    q.tables = h->dTables; q.ell = h->dEll;
     q.Z = dZ; q.delta = ddelta; q.jac = djac; q.trace = h->dTrace2;
     int maxg = std::min(pb2::kU8MaxGroups, pb2::kU8MaxThreads / (32 * q.gw));
     while (maxg > 1 && pb2::u8_layout(q, maxg) > kSmemLimit) --maxg;
@@ -216,7 +217,7 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
     q.zlen = p.D + p.x_off + 128;
     q.ntiles = 2 + 2 * p.m + p.m * (p.m + 1) / 2;
     q.ncw = (q.ntiles + 1) / 2;
-    q.Gfrag = h->dGfrag; q.ell = h->dEll; q.norms = h->dNorms; q.tab = h->dTab;
+    q.tables = h->dTables; q.ell = h->dEll;
     q.Z = dZ; q.mu = dmu; q.hess = dhess;
     const size_t smem = pb2::u8h_layout(q);
     if (smem > kSmemLimit) return fail(PB2_EINVAL, "u8h hessian: knot column too large for the shared-memory staging");
@@ -405,6 +406,12 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
       for (int q = 0; q <= pb2::kMaxDeg; ++q) { tab[q] = theta[q]; tab[20 + q] = invfact[q]; }
       PB2_CUDA_H(cudaMalloc(&h->dTab, sizeof(tab)));
       PB2_CUDA_H(cudaMemcpy(h->dTab, tab, sizeof(tab), cudaMemcpyHostToDevice));
+      std::vector<double> tb(h->plan.gfrag);
+      tb.insert(tb.end(), h->plan.norms.begin(), h->plan.norms.end());
+      if (tb.size() % 2) tb.push_back(0.0);
+      tb.insert(tb.end(), tab, tab + 40);
+      PB2_CUDA_H(cudaMalloc(&h->dTables, tb.size() * sizeof(double)));
+      PB2_CUDA_H(cudaMemcpy(h->dTables, tb.data(), tb.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
     PB2_CUDA_H(cudaFuncSetAttribute(pb2::dmma_kernel(h->plan.NT, h->plan.W),
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
@@ -457,6 +464,7 @@ void pb2_destroy(pb2_handle* h) {
   if (h->dEll) cudaFree(h->dEll);
   if (h->dNorms) cudaFree(h->dNorms);
   if (h->dTab) cudaFree(h->dTab);
+  if (h->dTables) cudaFree(h->dTables);
   if (h->dTrace) cudaFree(h->dTrace);
   for (double* p : {h->hZ, h->hDelta, h->hJac, h->hMu, h->hHess})
     if (p) cudaFreeHost(p);
