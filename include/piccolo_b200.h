@@ -130,6 +130,39 @@ int pb2_expand_compact_async(pb2_handle* h, const double* dcompact, int64_t n_kn
 void* pb2_stream(const pb2_handle* h);
 int pb2_sync(pb2_handle* h);
 
+/* ---- linear knot constraints evaluated in the same callbacks -----------------
+ * DerivativeIntegrator(x, xdot, traj): r_k = x_{k+1} - x_k - dt_k xdot_k   (u -> du, du -> ddu;
+ *   src/control/templates/smooth_pulse_problem.jl:267-275, spline_pulse_problem.jl:363-366)
+ * time consistency: t_{k+1} - t_k - dt_k   (applied by DirectTrajOpt when :t and :dt exist,
+ *   smooth_pulse_problem.jl:277).
+ * One handle evaluates every pair of a trajectory in one launch.  Row order: pair-major (the order
+ * given), knot-major inside a pair, component fastest; time rows last.  Jacobian values per
+ * derivative row: d x_k[i] (-1), d xdot_k[i] (-dt_k), d dt_k (-xdot_k[i]), d x_{k+1}[i] (+1); per
+ * time row: d t_k (-1), d dt_k (-1), d t_{k+1} (+1).  Hessian of sum mu.r: one entry per derivative
+ * row, (xdot_k[i], dt_k) = -mu (upper triangle).  Rows / columns 1-based like pb2_structure_*;
+ * rows are local to this handle (the caller offsets them into the NLP's constraint vector). */
+#define PB2_AUX_MAX_PAIRS 8
+typedef struct pb2_aux_desc {
+  int32_t K, D, dt_off;
+  int32_t t_off;                       /* < 0: no time-consistency rows */
+  int32_t global_dim;
+  int32_t n_pairs;
+  int32_t x_off[PB2_AUX_MAX_PAIRS], xdot_off[PB2_AUX_MAX_PAIRS], dim[PB2_AUX_MAX_PAIRS];
+  int32_t device;
+} pb2_aux_desc;
+typedef struct pb2_aux pb2_aux;
+int pb2_aux_create(const pb2_aux_desc* desc, pb2_aux** out);
+void pb2_aux_destroy(pb2_aux* h);
+int64_t pb2_aux_dim(const pb2_aux* h);
+int64_t pb2_aux_nnz_jac(const pb2_aux* h);
+int64_t pb2_aux_nnz_hess(const pb2_aux* h);
+int pb2_aux_structure_jac(const pb2_aux* h, int64_t* rows, int64_t* cols);
+int pb2_aux_structure_hess(const pb2_aux* h, int64_t* rows, int64_t* cols);
+/* delta / vals may be NULL to skip that output */
+int pb2_aux_residual_jacobian(pb2_aux* h, const double* Z, double* delta, double* vals, int space);
+int pb2_aux_hess_lagrangian(pb2_aux* h, const double* mu, double* vals, int space);
+int pb2_aux_residual_jacobian_async(pb2_aux* h, const double* dZ, double* ddelta, double* dvals, void* stream);
+
 /* pinned host memory for callers that want DMA without the staging copy */
 int pb2_host_alloc(void** ptr, int64_t bytes);
 int pb2_host_free(void* ptr);

@@ -21,7 +21,7 @@ from .generators import (  # noqa: F401
     density_lift_matrix, density_projection_matrix,
 )
 from .integrators import (  # noqa: F401
-    B200BilinearIntegrator, BilinearIntegrator, DensityTrajectory, KetTrajectory,
+    B200BilinearIntegrator, B200KnotLinearConstraints, BilinearIntegrator, DensityTrajectory, KetTrajectory,
     NamedTrajectory, OpenQuantumSystem, QuantumSystem, UnitaryTrajectory,
     eval_jacobian, evaluate_, hessian_of_lagrangian, hessian_structure, jacobian_structure,
 )

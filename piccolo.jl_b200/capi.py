@@ -19,6 +19,9 @@ SYMBOLS = [
     "pb2_structure_hess", "pb2_residual", "pb2_jacobian", "pb2_residual_jacobian",
     "pb2_hess_lagrangian", "pb2_residual_jacobian_async", "pb2_hess_lagrangian_async",
     "pb2_compact_stride", "pb2_residual_jacobian_compact_async", "pb2_expand_compact_async",
+    "pb2_aux_create", "pb2_aux_destroy", "pb2_aux_dim", "pb2_aux_nnz_jac", "pb2_aux_nnz_hess",
+    "pb2_aux_structure_jac", "pb2_aux_structure_hess", "pb2_aux_residual_jacobian", "pb2_aux_hess_lagrangian",
+    "pb2_aux_residual_jacobian_async",
     "pb2_stream", "pb2_sync", "pb2_host_alloc", "pb2_host_free", "pb2_launch_count",
 ]
 
@@ -37,6 +40,18 @@ class pb2_desc(ctypes.Structure):
         ("global_dim", ctypes.c_int32), ("knot0", ctypes.c_int64), ("device", ctypes.c_int32),
         ("algorithm", ctypes.c_int32), ("G0", ctypes.POINTER(ctypes.c_double)),
         ("Gj", ctypes.POINTER(ctypes.c_double)),
+    ]
+
+
+PB2_AUX_MAX_PAIRS = 8
+
+
+class pb2_aux_desc(ctypes.Structure):
+    _fields_ = [
+        ("K", ctypes.c_int32), ("D", ctypes.c_int32), ("dt_off", ctypes.c_int32), ("t_off", ctypes.c_int32),
+        ("global_dim", ctypes.c_int32), ("n_pairs", ctypes.c_int32),
+        ("x_off", ctypes.c_int32 * PB2_AUX_MAX_PAIRS), ("xdot_off", ctypes.c_int32 * PB2_AUX_MAX_PAIRS),
+        ("dim", ctypes.c_int32 * PB2_AUX_MAX_PAIRS), ("device", ctypes.c_int32),
     ]
 
 
@@ -84,6 +99,17 @@ def load_library():
     L.pb2_expand_compact_async.argtypes = [H, vp, ctypes.c_int64, vp, vp, vp]
     L.pb2_stream.argtypes = [H]
     L.pb2_stream.restype = ctypes.c_void_p
+    L.pb2_aux_create.argtypes = [ctypes.POINTER(pb2_aux_desc), ctypes.POINTER(H)]
+    L.pb2_aux_destroy.argtypes = [H]
+    L.pb2_aux_destroy.restype = None
+    for f in ("pb2_aux_dim", "pb2_aux_nnz_jac", "pb2_aux_nnz_hess"):
+        getattr(L, f).argtypes = [H]
+        getattr(L, f).restype = ctypes.c_int64
+    L.pb2_aux_structure_jac.argtypes = [H, ip, ip]
+    L.pb2_aux_structure_hess.argtypes = [H, ip, ip]
+    L.pb2_aux_residual_jacobian.argtypes = [H, vp, vp, vp, ctypes.c_int]
+    L.pb2_aux_hess_lagrangian.argtypes = [H, vp, vp, ctypes.c_int]
+    L.pb2_aux_residual_jacobian_async.argtypes = [H, vp, vp, vp, vp]
     L.pb2_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_int64]
     L.pb2_host_free.argtypes = [vp]
     _lib = L

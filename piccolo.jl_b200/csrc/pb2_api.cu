@@ -21,6 +21,7 @@
 #include "knot_dmma.cuh"
 #include "knot_u8.cuh"
 #include "knot_u8h.cuh"
+#include "knot_aux.cuh"
 
 namespace {
 
@@ -682,6 +683,187 @@ int pb2_host_alloc(void** ptr, int64_t bytes) {
 int pb2_host_free(void* ptr) {
   if (!ptr) return PB2_OK;
   PB2_CUDA(cudaFreeHost(ptr));
+  return PB2_OK;
+}
+
+
+// ---- linear knot constraints (DerivativeIntegrator pairs + time consistency) -----------------------
+struct pb2_aux {
+  pb2_aux_desc d{};
+  pb2::AuxParams p{};
+  cudaStream_t stream = nullptr;
+  double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
+  int64_t n_der = 0, n_time = 0;
+};
+
+int pb2_aux_create(const pb2_aux_desc* desc, pb2_aux** out) {
+  if (!desc || !out) return fail(PB2_EINVAL, "pb2_aux_create: null argument");
+  *out = nullptr;
+  const pb2_aux_desc& d = *desc;
+  if (d.K < 1 || d.D < 1 || d.n_pairs < 0 || d.n_pairs > PB2_AUX_MAX_PAIRS)
+    return fail(PB2_EINVAL, "pb2_aux_create: bad sizes");
+  auto inside = [&](int off, int len) { return off >= 0 && len >= 1 && off + len <= d.D; };
+  if (!inside(d.dt_off, 1) || (d.t_off >= 0 && !inside(d.t_off, 1)))
+    return fail(PB2_EINVAL, "pb2_aux_create: timestep / time offsets outside the knot column");
+  for (int i = 0; i < d.n_pairs; ++i)
+    if (!inside(d.x_off[i], d.dim[i]) || !inside(d.xdot_off[i], d.dim[i]))
+      return fail(PB2_EINVAL, "pb2_aux_create: component offsets outside the knot column");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(PB2_ENODEVICE, "pb2_aux_create: no CUDA device (this library has no CPU path)");
+  }
+  if (d.device < 0 || d.device >= ndev) return fail(PB2_EINVAL, "pb2_aux_create: bad device ordinal");
+  PB2_CUDA(cudaSetDevice(d.device));
+  pb2_aux* h = new (std::nothrow) pb2_aux();
+  if (!h) return fail(PB2_ENOMEM, "pb2_aux_create: out of memory");
+  h->d = d;
+  pb2::AuxParams& p = h->p;
+  p.K = d.K; p.D = d.D; p.dt_off = d.dt_off; p.t_off = d.t_off; p.n_pairs = d.n_pairs;
+  const long long nk = d.K - 1;
+  long long row = 0;
+  for (int i = 0; i < d.n_pairs; ++i) {
+    p.x_off[i] = d.x_off[i]; p.xdot_off[i] = d.xdot_off[i]; p.dim[i] = d.dim[i];
+    p.row0[i] = row;
+    row += nk * d.dim[i];
+  }
+  p.row0[d.n_pairs] = row;
+  h->n_der = row;
+  h->n_time = d.t_off >= 0 ? nk : 0;
+  p.n_rows = row + h->n_time;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return fail(PB2_ECUDA, "pb2_aux_create: cudaStreamCreate failed");
+  }
+  *out = h;
+  return PB2_OK;
+}
+
+void pb2_aux_destroy(pb2_aux* h) {
+  if (!h) return;
+  cudaSetDevice(h->d.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (double* q : {h->dZ, h->dDelta, h->dJac, h->dMu, h->dHess})
+    if (q) cudaFree(q);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaGetLastError();
+  delete h;
+}
+
+int64_t pb2_aux_dim(const pb2_aux* h) { return h ? h->p.n_rows : -1; }
+int64_t pb2_aux_nnz_jac(const pb2_aux* h) { return h ? 4 * h->n_der + 3 * h->n_time : -1; }
+int64_t pb2_aux_nnz_hess(const pb2_aux* h) { return h ? h->n_der : -1; }
+
+int pb2_aux_structure_jac(const pb2_aux* h, int64_t* rows, int64_t* cols) {
+  if (!h || !rows || !cols) return fail(PB2_EINVAL, "pb2_aux_structure_jac: null argument");
+  const pb2_aux_desc& d = h->d;
+  const int64_t nk = d.K - 1, D = d.D;
+  int64_t o = 0, r = 1;
+  for (int pr = 0; pr < d.n_pairs; ++pr)
+    for (int64_t k = 0; k < nk; ++k)
+      for (int64_t i = 0; i < d.dim[pr]; ++i, ++r) {
+        const int64_t c0 = k * D + 1;
+        rows[o] = r; cols[o++] = c0 + d.x_off[pr] + i;
+        rows[o] = r; cols[o++] = c0 + d.xdot_off[pr] + i;
+        rows[o] = r; cols[o++] = c0 + d.dt_off;
+        rows[o] = r; cols[o++] = c0 + D + d.x_off[pr] + i;
+      }
+  if (d.t_off >= 0)
+    for (int64_t k = 0; k < nk; ++k, ++r) {
+      const int64_t c0 = k * D + 1;
+      rows[o] = r; cols[o++] = c0 + d.t_off;
+      rows[o] = r; cols[o++] = c0 + d.dt_off;
+      rows[o] = r; cols[o++] = c0 + D + d.t_off;
+    }
+  return PB2_OK;
+}
+
+int pb2_aux_structure_hess(const pb2_aux* h, int64_t* rows, int64_t* cols) {
+  if (!h || !rows || !cols) return fail(PB2_EINVAL, "pb2_aux_structure_hess: null argument");
+  const pb2_aux_desc& d = h->d;
+  const int64_t nk = d.K - 1, D = d.D;
+  int64_t o = 0;
+  for (int pr = 0; pr < d.n_pairs; ++pr)
+    for (int64_t k = 0; k < nk; ++k)
+      for (int64_t i = 0; i < d.dim[pr]; ++i) {
+        const int64_t a = k * D + 1 + d.xdot_off[pr] + i, c = k * D + 1 + d.dt_off;
+        rows[o] = std::min(a, c);
+        cols[o++] = std::max(a, c);
+      }
+  return PB2_OK;
+}
+
+static int aux_launch(pb2_aux* h, const double* dZ, const double* dmu, double* ddelta, double* djac, double* dhess,
+                      cudaStream_t st) {
+  if (h->p.n_rows <= 0) return PB2_OK;
+  pb2::AuxParams p = h->p;
+  p.Z = dZ; p.mu = dmu; p.delta = ddelta; p.jac = djac; p.hess = dhess;
+  const int blocks = (int)std::min<long long>((p.n_rows + 255) / 256, 148 * 8);
+  pb2::knot_aux_kernel<<<blocks, 256, 0, st>>>(p);
+  PB2_CUDA(cudaGetLastError());
+  return PB2_OK;
+}
+
+int pb2_aux_residual_jacobian_async(pb2_aux* h, const double* dZ, double* ddelta, double* dvals, void* stream) {
+  if (!h || !dZ) return fail(PB2_EINVAL, "pb2_aux_residual_jacobian_async: null argument");
+  PB2_CUDA(cudaSetDevice(h->d.device));
+  return aux_launch(h, dZ, nullptr, ddelta, dvals, nullptr, (cudaStream_t)stream);
+}
+
+static int aux_ensure(double** dev, size_t n) {
+  if (!*dev) PB2_CUDA(cudaMalloc(dev, std::max<size_t>(n, 1) * sizeof(double)));
+  return PB2_OK;
+}
+
+int pb2_aux_residual_jacobian(pb2_aux* h, const double* Z, double* delta, double* vals, int space) {
+  if (!h || !Z) return fail(PB2_EINVAL, "pb2_aux_residual_jacobian: null argument");
+  PB2_CUDA(cudaSetDevice(h->d.device));
+  if (space == PB2_DEVICE) {
+    int rc = aux_launch(h, Z, nullptr, delta, vals, nullptr, h->stream);
+    if (rc) return rc;
+    PB2_CUDA(cudaStreamSynchronize(h->stream));
+    return PB2_OK;
+  }
+  if (space != PB2_HOST) return fail(PB2_EINVAL, "pb2_aux_residual_jacobian: bad space");
+  const size_t nZ = (size_t)h->d.D * h->d.K, nD = (size_t)h->p.n_rows, nJ = (size_t)pb2_aux_nnz_jac(h);
+  int rc;
+  if ((rc = aux_ensure(&h->dZ, nZ)) || (delta && (rc = aux_ensure(&h->dDelta, nD))) ||
+      (vals && (rc = aux_ensure(&h->dJac, nJ))))
+    return rc;
+  PB2_CUDA(cudaMemcpyAsync(h->dZ, Z, nZ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = aux_launch(h, h->dZ, nullptr, delta ? h->dDelta : nullptr, vals ? h->dJac : nullptr, nullptr, h->stream)))
+    return rc;
+  if (delta) PB2_CUDA(cudaMemcpyAsync(delta, h->dDelta, nD * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (vals) PB2_CUDA(cudaMemcpyAsync(vals, h->dJac, nJ * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PB2_CUDA(cudaStreamSynchronize(h->stream));
+  return PB2_OK;
+}
+
+int pb2_aux_hess_lagrangian(pb2_aux* h, const double* mu, double* vals, int space) {
+  if (!h || !mu || !vals) return fail(PB2_EINVAL, "pb2_aux_hess_lagrangian: null argument");
+  PB2_CUDA(cudaSetDevice(h->d.device));
+  if (h->n_der <= 0) return PB2_OK;
+  pb2::AuxParams p = h->p;
+  p.n_rows = h->n_der;   // time rows have no second derivatives
+  p.Z = nullptr; p.delta = nullptr; p.jac = nullptr;
+  const int blocks = (int)std::min<long long>((p.n_rows + 255) / 256, 148 * 8);
+  if (space == PB2_DEVICE) {
+    p.mu = mu; p.hess = vals;
+    pb2::knot_aux_kernel<<<blocks, 256, 0, h->stream>>>(p);
+    PB2_CUDA(cudaGetLastError());
+    PB2_CUDA(cudaStreamSynchronize(h->stream));
+    return PB2_OK;
+  }
+  if (space != PB2_HOST) return fail(PB2_EINVAL, "pb2_aux_hess_lagrangian: bad space");
+  const size_t n = (size_t)h->n_der;
+  int rc;
+  if ((rc = aux_ensure(&h->dMu, (size_t)h->p.n_rows)) || (rc = aux_ensure(&h->dHess, n))) return rc;
+  PB2_CUDA(cudaMemcpyAsync(h->dMu, mu, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  p.mu = h->dMu; p.hess = h->dHess;
+  pb2::knot_aux_kernel<<<blocks, 256, 0, h->stream>>>(p);
+  PB2_CUDA(cudaGetLastError());
+  PB2_CUDA(cudaMemcpyAsync(vals, h->dHess, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PB2_CUDA(cudaStreamSynchronize(h->stream));
   return PB2_OK;
 }
 

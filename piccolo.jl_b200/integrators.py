@@ -243,6 +243,75 @@ class B200BilinearIntegrator:
         return int(self._lib.pb2_launch_count(self._h))
 
 
+class B200KnotLinearConstraints:
+    """Every ``DerivativeIntegrator(x, xdot, traj)`` of a problem plus the time-consistency constraint,
+    evaluated by one launch (smooth_pulse_problem.jl:267-277; include/piccolo_b200.h for the orders)."""
+
+    def __init__(self, traj, pairs=(("u", "du"), ("du", "ddu")), time_consistency=True, device=0):
+        self._lib = capi.load_library()
+        comps = traj.components
+        d = capi.pb2_aux_desc()
+        d.K, d.D, d.dt_off = traj.N, traj.dim, comps[traj.timestep].start
+        d.t_off = comps["t"].start if (time_consistency and "t" in comps) else -1
+        d.global_dim, d.n_pairs, d.device = traj.global_dim, len(pairs), device
+        if len(pairs) > capi.PB2_AUX_MAX_PAIRS:
+            raise ValueError("too many derivative pairs")
+        self.pairs = []
+        for i, (x, xd) in enumerate(pairs):
+            if len(comps[x]) != len(comps[xd]):
+                raise ValueError(f"components {x} and {xd} differ in size")
+            d.x_off[i], d.xdot_off[i], d.dim[i] = comps[x].start, comps[xd].start, len(comps[x])
+            self.pairs.append((comps[x].start, comps[xd].start, len(comps[x])))
+        self.dt_off, self.t_off = d.dt_off, (d.t_off if d.t_off >= 0 else None)
+        self.K, self.D = traj.N, traj.dim
+        h = ctypes.c_void_p()
+        capi.check(self._lib.pb2_aux_create(ctypes.byref(d), ctypes.byref(h)))
+        self._h = h
+        self.dim = int(self._lib.pb2_aux_dim(h))
+        self.nnz_jac = int(self._lib.pb2_aux_nnz_jac(h))
+        self.nnz_hess = int(self._lib.pb2_aux_nnz_hess(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pb2_aux_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _structure(self, fn, n):
+        rows, cols = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+        ip = ctypes.POINTER(ctypes.c_int64)
+        capi.check(fn(self._h, rows.ctypes.data_as(ip), cols.ctypes.data_as(ip)))
+        return rows, cols
+
+    def jacobian_structure(self):
+        return self._structure(self._lib.pb2_aux_structure_jac, self.nnz_jac)
+
+    def hessian_structure(self):
+        return self._structure(self._lib.pb2_aux_structure_hess, self.nnz_hess)
+
+    def residual_jacobian(self, Z):
+        Z = Z.data if isinstance(Z, NamedTrajectory) else np.asfortranarray(Z, dtype=np.float64)
+        if Z.shape != (self.D, self.K):
+            raise ValueError(f"trajectory is {Z.shape}, expected {(self.D, self.K)}")
+        delta, vals = np.empty(self.dim), np.empty(self.nnz_jac)
+        capi.check(self._lib.pb2_aux_residual_jacobian(self._h, Z.ctypes.data, delta.ctypes.data, vals.ctypes.data,
+                                                       capi.PB2_HOST))
+        return delta, vals
+
+    def hessian_values(self, mu):
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        if mu.size < self.nnz_hess:
+            raise ValueError("mu must cover the derivative rows")
+        out = np.empty(self.nnz_hess)
+        capi.check(self._lib.pb2_aux_hess_lagrangian(self._h, mu.ctypes.data, out.ctypes.data, capi.PB2_HOST))
+        return out
+
+    def residual_jacobian_device(self, dZ, ddelta, dvals, stream=None):
+        capi.check(self._lib.pb2_aux_residual_jacobian_async(self._h, _as_ptr(dZ), _as_ptr(ddelta), _as_ptr(dvals),
+                                                             _as_ptr(stream)))
+
+
 def BilinearIntegrator(qtraj, traj_or_N, traj=None, **kw):
     """BilinearIntegrator(qtraj, N) -- dispatch on the trajectory type (integrators.jl:35-95).
 

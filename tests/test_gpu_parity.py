@@ -446,3 +446,29 @@ def test_u8_hessian_kernel_substeps_many_knots_and_general_kernel(monkeypatch):
     hg = Bg.hessian_values(Z, mu)
     assert np.abs(hg.reshape(p.K - 1, -1)[small] - H[small]).max() < 1e-10 * np.abs(H[small]).max()
     Bg.close()
+
+
+def test_linear_knot_constraints_match_oracle_and_golden():
+    """DerivativeIntegrator pairs + time consistency through the C ABI."""
+    from oracle import linear as LN
+    p, Zg = GU.load("two_qubit_zoh")
+    rng = np.random.default_rng(5)
+    for Z in (Zg, np.asfortranarray(Zg + 0.01 * rng.standard_normal(Zg.shape))):
+        traj = pb.NamedTrajectory.smooth_pulse_layout(Z, p.n_x, p.m, "Ũ⃗")
+        L = pb.B200KnotLinearConstraints(traj)
+        pairs, dt_off, t_off = L.pairs, L.dt_off, L.t_off
+        d, v = L.residual_jacobian(Z)
+        assert np.array_equal(d, LN.residual(Z, pairs, dt_off, t_off))
+        ro, co, vo = LN.jacobian(Z, pairs, dt_off, t_off)
+        r, c = L.jacobian_structure()
+        assert np.array_equal(r, ro) and np.array_equal(c, co) and np.array_equal(v, vo)
+        mu = rng.standard_normal(L.dim)
+        hr, hc, hv = LN.hessian(Z, mu, pairs, dt_off)
+        r, c = L.hessian_structure()
+        assert np.array_equal(r, hr) and np.array_equal(c, hc) and np.array_equal(L.hessian_values(mu), hv)
+        L.close()
+    traj = pb.NamedTrajectory.smooth_pulse_layout(Zg, p.n_x, p.m, "Ũ⃗")
+    L = pb.B200KnotLinearConstraints(traj)
+    d, _ = L.residual_jacobian(Zg)
+    assert np.abs(d).max() < 1e-12          # the reference's converged solution satisfies them
+    L.close()

@@ -152,3 +152,32 @@ def test_structure_counts():
         r, c = KN.jacobian_structure(p)
         assert r.dtype == np.int64 and r.min() == 1 and r.max() == p.dim
         assert len(set(zip(r.tolist(), c.tolist()))) == r.size    # no duplicates emitted
+
+
+def test_linear_knot_constraints_on_reference_golden():
+    """DerivativeIntegrator (u->du, du->ddu) and time consistency: the reference's converged C2
+    solution satisfies them (<= 3e-14 / 2e-15); Jacobian against finite differences."""
+    from oracle import linear as LN
+    from tests import golden_util as GU
+    p, Z = GU.load("two_qubit_zoh")
+    m, n_x = p.m, p.n_x
+    u, du, ddu = n_x + 2, n_x + 2 + m, n_x + 2 + 2 * m
+    pairs = [(u, du, m), (du, ddu, m)]
+    r = LN.residual(Z, pairs, dt_off=n_x, t_off=n_x + 1)
+    assert r.size == (2 * m + 1) * (p.K - 1)
+    assert np.abs(r[:2 * m * (p.K - 1)]).max() < 1e-12 and np.abs(r[2 * m * (p.K - 1):]).max() < 1e-13
+    rows, cols, vals = LN.jacobian(Z, pairs, n_x, n_x + 1)
+    rng = np.random.default_rng(3)
+    dZ = rng.standard_normal(Z.shape)
+    h = 1e-6
+    fd = (LN.residual(Z + h * dZ, pairs, n_x, n_x + 1) - LN.residual(Z - h * dZ, pairs, n_x, n_x + 1)) / (2 * h)
+    jv = np.zeros(r.size)
+    np.add.at(jv, rows - 1, vals * dZ.reshape(-1, order="F")[cols - 1])
+    assert np.abs(jv - fd).max() < 1e-8
+    mu = rng.standard_normal(r.size)
+    hr, hc, hv = LN.hessian(Z, mu, pairs, n_x)
+    # second directional derivative of mu . r along dZ equals dZ^T H dZ (H symmetric from its upper triangle)
+    f = lambda t: mu @ LN.residual(Z + t * dZ, pairs, n_x, n_x + 1)
+    d2 = (f(1e-3) - 2 * f(0.0) + f(-1e-3)) / 1e-6
+    z = dZ.reshape(-1, order="F")
+    assert abs(2 * np.sum(hv * z[hr - 1] * z[hc - 1]) - d2) < 1e-6 * max(1.0, abs(d2))
