@@ -22,7 +22,7 @@ from .generators import (  # noqa: F401
 )
 from .integrators import (  # noqa: F401
     B200BilinearIntegrator, B200KnotLinearConstraints, BilinearIntegrator, DensityTrajectory, KetTrajectory,
-    NamedTrajectory, OpenQuantumSystem, QuantumSystem, UnitaryTrajectory,
+    MultiKetTrajectory, NamedTrajectory, OpenQuantumSystem, QuantumSystem, SamplingTrajectory, UnitaryTrajectory,
     eval_jacobian, evaluate_, hessian_of_lagrangian, hessian_structure, jacobian_structure,
 )
 from .sharding import ShardedBilinearIntegrator, knot_partition  # noqa: F401

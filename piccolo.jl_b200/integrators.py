@@ -70,6 +70,20 @@ class NamedTrajectory:
         return self.data.reshape(-1, order="F")
 
     @classmethod
+    def multi_state_layout(cls, data, state_names, n_x_each, m, derivs=2):
+        """[state_1 | state_2 | ... | Δt | t | u | du | ddu]  (multi-ket / sampling trajectories)."""
+        comps, o = {}, 0
+        for name in state_names:
+            comps[name] = range(o, o + n_x_each)
+            o += n_x_each
+        comps["Δt"], comps["t"], comps["u"] = range(o, o + 1), range(o + 1, o + 2), range(o + 2, o + 2 + m)
+        o += 2 + m
+        for name in ["du", "ddu", "dddu"][:derivs]:
+            comps[name] = range(o, o + m)
+            o += m
+        return cls(data, comps)
+
+    @classmethod
     def smooth_pulse_layout(cls, data, n_x, m, state_name, derivs=2):
         """[state | Δt | t | u | du | ddu]   (smooth_pulse_problem.jl:196-201)."""
         comps = {state_name: range(0, n_x), "Δt": range(n_x, n_x + 1), "t": range(n_x + 1, n_x + 2),
@@ -96,6 +110,26 @@ class KetTrajectory(_QTraj):
 
 class DensityTrajectory(_QTraj):
     kind, state_name = "density", "ρ⃗̃"
+
+
+class MultiKetTrajectory(_QTraj):
+    """Several kets driven by one system and one control row: one integrator per state
+    (integrators.jl:102-117); state components ψ̃1, ψ̃2, ... precede the shared [Δt | t | u ...]
+    tail (named_trajectory_conversion.jl:465-)."""
+    kind = "ket"
+
+    def __init__(self, system, n_states):
+        super().__init__(system)
+        self.state_names = [f"ψ̃{i + 1}" for i in range(n_states)]
+
+
+class SamplingTrajectory:
+    """An ensemble of systems sharing the controls: one integrator per member, each with its own
+    generator (integrators.jl:134-226; sampling_trajectory.jl:97-126, 306-349)."""
+
+    def __init__(self, base_qtraj_type, systems):
+        self.kind, self.systems = base_qtraj_type.kind, list(systems)
+        self.state_names = [f"{base_qtraj_type.state_name}{i + 1}" for i in range(len(self.systems))]
 
 
 # ----------------------------------------------------------------------------- #
@@ -319,6 +353,18 @@ def BilinearIntegrator(qtraj, traj_or_N, traj=None, **kw):
     the reference rebuilds it from ``qtraj`` and ``N``, here it is passed in."""
     if isinstance(traj_or_N, NamedTrajectory):
         traj = traj_or_N
+    if isinstance(qtraj, (MultiKetTrajectory, SamplingTrajectory)) and traj is not None:
+        # a vector of integrators, one per state block, all reading the same Δt / u rows
+        systems = qtraj.systems if isinstance(qtraj, SamplingTrajectory) else [qtraj.system] * len(qtraj.state_names)
+        comps = traj.components
+        out = []
+        for name, sys_ in zip(qtraj.state_names, systems):
+            G0, Gj = sys_.G_parts()
+            out.append(B200BilinearIntegrator(
+                qtraj.kind, G0, Gj, K=traj.N, D=traj.dim, x_off=comps[name].start,
+                dt_off=comps[traj.timestep].start, u_off=comps["u"].start, x_name=name,
+                global_dim=traj.global_dim, **kw))
+        return out
     if traj is None:
         raise TypeError("pass the NamedTrajectory that defines the knot layout")
     if not isinstance(traj_or_N, NamedTrajectory) and int(traj_or_N) != traj.N:

@@ -54,6 +54,14 @@ SPECS = {
         x0=iso.operator_to_iso_vec(np.eye(2)),
         system="QuantumSystem(Z,[X,Y],[1,1])",
         source="docs/literate/concepts/trajectories.jl:38-57", tight=False),
+    # MultiKetTrajectory: two kets sharing one generator and one control row; knot column
+    # [psi1 (4) | psi2 (4) | dt | t | u | du | ddu]  (one BilinearIntegrator per state,
+    # src/control/integrators.jl:102-117).  Stopped at max_iter = 50: a valid input, not a delta ~ 0 KAT.
+    "trajectories_multi": dict(
+        file="trajectories_multi_573ffb2.jld2", kind="multiket", d=2, m=2, K=100, n_states=2,
+        x0=np.concatenate([iso.ket_to_iso(np.array([1.0, 0.0])), iso.ket_to_iso(np.array([0.0, 1.0]))]),
+        system="QuantumSystem(Z,[X,Y],[1,1]); MultiKetTrajectory(sys, pulse, [|0>,|1>], [|1>,|0>])",
+        source="docs/literate/concepts/trajectories.jl:86-113", tight=False),
 }
 
 
@@ -63,7 +71,7 @@ def n_x_of(kind, d):
 
 def extract(spec):
     raw = open(os.path.join(DATA, spec["file"]), "rb").read()
-    n_x = n_x_of(spec["kind"], spec["d"])
+    n_x = 2 * spec["d"] * spec["n_states"] if spec["kind"] == "multiket" else n_x_of(spec["kind"], spec["d"])
     D = n_x + 2 + 3 * spec["m"]
     K = spec["K"]
     pat = np.asarray(spec["x0"], dtype="<f8").tobytes()

@@ -18,6 +18,8 @@ TIGHT = {  # max |delta| the reference's converged solution leaves, 
 
 
 def load(name):
+    if name == "trajectories_multi":
+        raise ValueError("multi-state fixture: use load_multi()")
     Z = np.load(os.path.join(GOLDEN, name + ".npz"))["Z"]
     Z = np.asfortranarray(Z)
     K = META[name]["K"]
@@ -41,3 +43,18 @@ def load(name):
         p = KN.make_problem("ket" if name == "trajectories_ket" else "unitary", G0, Gj, K)
     assert p.D == Z.shape[0] and p.K == Z.shape[1]
     return p, Z
+
+
+def load_multi():
+    """The reference's MultiKetTrajectory solution: (list of per-state KnotProblems, Z).  Every state
+    block has its own integrator; they share the Δt / u rows (integrators.jl:102-117)."""
+    import dataclasses
+    Z = np.asfortranarray(np.load(os.path.join(GOLDEN, "trajectories_multi.npz"))["Z"])
+    meta = META["trajectories_multi"]
+    s = S.QuantumSystem(S.PAULI_Z, [S.PAULI_X, S.PAULI_Y], [1, 1])
+    G0, Gj = s.G_parts()
+    base = KN.make_problem("ket", G0, Gj, meta["K"])
+    n_s, b = meta["n_states"], base.b
+    probs = [dataclasses.replace(base, D=Z.shape[0], x_off=i * b, dt_off=n_s * b, u_off=n_s * b + 2)
+             for i in range(n_s)]
+    return probs, Z

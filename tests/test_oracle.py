@@ -181,3 +181,14 @@ def test_linear_knot_constraints_on_reference_golden():
     d2 = (f(1e-3) - 2 * f(0.0) + f(-1e-3)) / 1e-6
     z = dZ.reshape(-1, order="F")
     assert abs(2 * np.sum(hv * z[hr - 1] * z[hc - 1]) - d2) < 1e-6 * max(1.0, abs(d2))
+
+
+def test_multi_ket_golden_is_a_valid_input():
+    """The reference's MultiKetTrajectory solution (stopped at max_iter): every state block obeys its own
+    dynamics constraint to the reference's solve-level tolerance, with the shared control rows."""
+    probs, Z = GU.load_multi()
+    assert Z.shape == (16, 100) and len(probs) == 2
+    for p in probs:
+        d = KN.residual(p, Z)
+        assert np.abs(d).max() < 1e-2                      # smooth_pulse_problem.jl:781-784
+        assert np.abs(d - CP.residual(p, Z)).max() < 1e-12  # both oracle algorithms agree on it
