@@ -32,7 +32,8 @@ struct U8Params {
   int gw;                // warps per group: producer + (E,X) + ceil(m/2) jet warps
   int stagger;           // cycles by which a group with fewer knots than group 0 delays its start
   int stagger_g;         // additional delay of group g: g * stagger_g cycles
-  int compact;           // 1: write [E once | jets, d/d dt, ones | delta] records of cstride doubles to `jac`
+  int compact;           // 1: [E once | jets, d/d dt, ones | delta] records of cstride doubles go to `jac`;
+                         // 2: host records [E columns 0..7 | jets, d/d dt | delta]
   int cstride;
   int dry;               // debug: 1 = exit after the prologue, 2 = exit immediately (launch-floor measurement)
   // shared-memory layout in doubles (u8_layout)
@@ -315,7 +316,14 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (p.compact) {
+          if (p.compact == 2) {
+            // host record = [E columns 0..7 (128) | jets, d/d dt | delta]: the least that has to cross
+            // PCIe (the other half of E is its mirror image, the identity entries are constant)
+            double* rec = p.jac + (size_t)kprev * p.cstride;
+            bulk_s2g(rec, a_stage, 1024u);
+            bulk_s2g(rec + 128, a_stage + o_J, (uint32_t)(m + 1) * 1024u);
+            bulk_s2g(rec + 128 + (m + 1) * 128, a_stage + o_D, 1024u);
+          } else if (p.compact) {
             // record = [E (256) | jets, d/d dt, ones | delta]: what crosses NVLink in a sharded run
             double* rec = p.jac + (size_t)kprev * p.cstride;
             bulk_s2g(rec, a_stage, 2048u);

@@ -8,12 +8,15 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
+#include <functional>
 #include <vector>
 
 #include "../../include/piccolo_b200.h"
@@ -22,6 +25,7 @@
 #include "knot_u8.cuh"
 #include "knot_u8h.cuh"
 #include "knot_aux.cuh"
+#include "host_pool.h"
 
 namespace {
 
@@ -91,6 +95,8 @@ struct pb2_handle {
   double* dGfrag = nullptr;
   double* dNorms = nullptr;
   double* dTab = nullptr;
+  double *dComp = nullptr, *hComp = nullptr;   // compact records: device buffer and pinned landing zone
+  cudaEvent_t chunk_ev[8] = {};
   double* dTables = nullptr;   // [gfrag | norms (even) | theta | 1/k!] contiguous, the u8 kernels' smem order
   long long* dTrace = nullptr;
   long long* dTrace2 = nullptr;
@@ -124,7 +130,7 @@ pb2::KnotParams make_params(const pb2_handle* h) {
   return p;
 }
 
-int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, bool compact = false) {
+int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, int compact = 0) {
   if (h->nk() <= 0) return PB2_OK;
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.delta = ddelta; p.jac = djac;
@@ -139,8 +145,8 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.gw = 2 + (p.m + 1) / 2;
     q.stagger = h->stagger;
     q.stagger_g = h->stagger_g;
-    q.compact = compact ? 1 : 0;
-    q.cstride = 256 + (p.m + 3) * 128;
+    q.compact = compact;
+    q.cstride = compact == 2 ? (p.m + 3) * 128 : 256 + (p.m + 3) * 128;
     if (const char* env = std::getenv("PB2_DRY")) q.dry = std::atoi(env);
     q.tables = h->dTables; q.ell = h->dEll;
     q.Z = dZ; q.delta = ddelta; q.jac = djac; q.trace = h->dTrace2;
@@ -466,6 +472,10 @@ void pb2_destroy(pb2_handle* h) {
   if (h->dNorms) cudaFree(h->dNorms);
   if (h->dTab) cudaFree(h->dTab);
   if (h->dTables) cudaFree(h->dTables);
+  if (h->dComp) cudaFree(h->dComp);
+  if (h->hComp) cudaFreeHost(h->hComp);
+  for (cudaEvent_t e : h->chunk_ev)
+    if (e) cudaEventDestroy(e);
   if (h->dTrace) cudaFree(h->dTrace);
   for (double* p : {h->hZ, h->hDelta, h->hJac, h->hMu, h->hHess})
     if (p) cudaFreeHost(p);
@@ -573,7 +583,7 @@ int pb2_residual_jacobian_compact_async(pb2_handle* h, const double* dZ, double*
   if (!dZ || !dcompact) return fail(PB2_EINVAL, "pb2_residual_jacobian_compact_async: null argument");
   if (pb2_compact_stride(h) == 0) return fail(PB2_EINVAL, "pb2_residual_jacobian_compact_async: unsupported for this handle");
   PB2_CUDA(cudaSetDevice(h->d.device));
-  return launch_resjac(h, dZ, nullptr, dcompact, (cudaStream_t)stream, true);
+  return launch_resjac(h, dZ, nullptr, dcompact, (cudaStream_t)stream, 1);
 }
 
 int pb2_expand_compact_async(pb2_handle* h, const double* dcompact, int64_t n_knots, double* ddelta, double* dvals,
@@ -623,6 +633,66 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
   if (space != PB2_HOST) return fail(PB2_EINVAL, "pb2_residual_jacobian: bad space");
   const size_t nZ = (size_t)h->d.D * h->d.K, nD = (size_t)pb2_dim(h), nJ = (size_t)pb2_nnz_jac(h);
   int rc;
+  if (vals && h->nk() > 0 && pb2_compact_stride(h) != 0 && !std::getenv("PB2_NO_COMPACT_D2H")) {
+    // 3-qubit unitary shape: the d/dx_k block is n_b copies of one b x b block, so only the compact
+    // record (9.2 KB instead of 23.5 KB per knot at C3) crosses PCIe; it lands in pinned memory in
+    // chunks, and host threads replicate each chunk into the caller's arrays (pb2_structure_jac
+    // order) while the next chunk is still in flight.  Data movement only.
+    const int64_t nk = h->nk(), cs = (int64_t)(h->d.m + 3) * 128;   // host record: [E cols 0..7 | jets, d/d dt | delta]
+    const int n_x = h->n_x(), bb = h->d.b * h->d.b, n_b = h->d.n_b, nJd = (h->d.m + 1) * n_x, nnz = h->nnz_jac_knot();
+    if ((rc = ensure(&h->dZ, &h->hZ, nZ))) return rc;
+    if ((rc = ensure(&h->dComp, &h->hComp, (size_t)(nk * cs)))) return rc;
+    if ((rc = stage_in(h, Z, h->hZ, h->dZ, nZ))) return rc;
+    if ((rc = launch_resjac(h, h->dZ, nullptr, h->dComp, h->stream, 2))) return rc;
+    const int nch = (int)std::min<int64_t>(8, std::max<int64_t>(1, nk / 32));
+    const int64_t per = (nk + nch - 1) / nch;
+    for (int c = 0; c < nch; ++c) {
+      const int64_t k0 = c * per, k1 = std::min(nk, k0 + per);
+      if (!h->chunk_ev[c]) PB2_CUDA(cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
+      if (k1 > k0)
+        PB2_CUDA(cudaMemcpyAsync(h->hComp + k0 * cs, h->dComp + k0 * cs, (size_t)(k1 - k0) * cs * sizeof(double),
+                                 cudaMemcpyDeviceToHost, h->stream));
+      PB2_CUDA(cudaEventRecord(h->chunk_ev[c], h->stream));
+    }
+    std::atomic<int> ready[8];
+    for (auto& r : ready) r.store(0, std::memory_order_relaxed);
+    std::atomic<int> failed{0};
+    const double* comp = h->hComp;
+    auto expand = [&](int64_t a, int64_t b) {
+      double E[256];
+      for (int64_t k = a; k < b; ++k) {
+        const int c = (int)(k / per);
+        while (!ready[c].load(std::memory_order_acquire))
+          if (failed.load(std::memory_order_relaxed)) return;
+        const double* src = comp + k * cs;
+        // -E = -[[P, -Q], [Q, P]]: column c + 8 is [-(rows 8..15 of column c); rows 0..7 of column c]
+        std::memcpy(E, src, 128 * sizeof(double));
+        for (int col = 0; col < 8; ++col)
+          for (int r = 0; r < 8; ++r) {
+            E[(col + 8) * 16 + r] = -src[col * 16 + 8 + r];
+            E[(col + 8) * 16 + 8 + r] = src[col * 16 + r];
+          }
+        double* out = vals + k * (int64_t)nnz;
+        for (int cp = 0; cp < n_b; ++cp) std::memcpy(out + (size_t)cp * bb, E, bb * sizeof(double));
+        out += (size_t)n_b * bb;
+        std::memcpy(out, src + 128, nJd * sizeof(double));
+        for (int i = 0; i < n_x; ++i) out[nJd + i] = 1.0;   // the constant d/dx_{k+1} identity entries
+        if (delta) std::memcpy(delta + k * n_x, src + 128 + nJd, n_x * sizeof(double));
+      }
+    };
+    // the pool's threads start un-packing as chunks land; this thread releases the chunks, then joins in
+    std::function<void(int64_t, int64_t)> fn = expand;
+    pb2::HostPool& pool = pb2::HostPool::instance();
+    pool.begin(nk, 4, fn);
+    for (int c = 0; c < nch; ++c) {
+      if (cudaEventSynchronize(h->chunk_ev[c]) != cudaSuccess) { failed.store(1); break; }
+      ready[c].store(1, std::memory_order_release);
+    }
+    pool.finish();
+    if (failed.load()) return fail(PB2_ECUDA, "pb2_residual_jacobian: device-to-host copy failed");
+    PB2_CUDA(cudaStreamSynchronize(h->stream));
+    return PB2_OK;
+  }
   if ((rc = ensure(&h->dZ, &h->hZ, nZ))) return rc;
   if (delta && (rc = ensure(&h->dDelta, &h->hDelta, nD))) return rc;
   if (vals && (rc = ensure(&h->dJac, &h->hJac, nJ))) return rc;
