@@ -96,7 +96,7 @@ struct pb2_handle {
   double* dNorms = nullptr;
   double* dTab = nullptr;
   double *dComp = nullptr, *hComp = nullptr;   // compact records: device buffer and pinned landing zone
-  cudaEvent_t chunk_ev[8] = {};
+  cudaEvent_t chunk_ev[16] = {};
   double* dTables = nullptr;   // [gfrag | norms (even) | theta | 1/k!] contiguous, the u8 kernels' smem order
   long long* dTrace = nullptr;
   long long* dTrace2 = nullptr;
@@ -644,7 +644,8 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
     if ((rc = ensure(&h->dComp, &h->hComp, (size_t)(nk * cs)))) return rc;
     if ((rc = stage_in(h, Z, h->hZ, h->dZ, nZ))) return rc;
     if ((rc = launch_resjac(h, h->dZ, nullptr, h->dComp, h->stream, 2))) return rc;
-    const int nch = (int)std::min<int64_t>(8, std::max<int64_t>(1, nk / 32));
+    const int nch_env = std::getenv("PB2_D2H_CHUNKS") ? std::atoi(std::getenv("PB2_D2H_CHUNKS")) : 8;
+    const int nch = (int)std::min<int64_t>(std::min(16, std::max(1, nch_env)), std::max<int64_t>(1, nk / 32));
     const int64_t per = (nk + nch - 1) / nch;
     for (int c = 0; c < nch; ++c) {
       const int64_t k0 = c * per, k1 = std::min(nk, k0 + per);
@@ -654,7 +655,7 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
                                  cudaMemcpyDeviceToHost, h->stream));
       PB2_CUDA(cudaEventRecord(h->chunk_ev[c], h->stream));
     }
-    std::atomic<int> ready[8];
+    std::atomic<int> ready[16];
     for (auto& r : ready) r.store(0, std::memory_order_relaxed);
     std::atomic<int> failed{0};
     const double* comp = h->hComp;
