@@ -169,8 +169,11 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # NCCL writes its version banner / debug lines to stdout; stdout carries the JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version banner / debug lines on stdout; stdout must carry the JSON line only,
+        # so file descriptor 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     p, Z, _ = C.trajectory(args.config)
@@ -349,7 +352,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src},
             "e2e": {"value": n_eval * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": 8 * p.D * p.K,
-                    "d2h_bytes_per_step": 8 * (p.m + 3) * 128 * n_eval if B.compact_stride else 8 * (B.dim + B.nnz_jac),
+                    "d2h_bytes_per_step": 8 * B.compact_stride * n_eval if B.compact_stride else 8 * (B.dim + B.nnz_jac),
                     "host_array_bytes_per_step": 8 * (B.dim + B.nnz_jac),
                     "steps": e2e_steps,
                     "note": "pb2_residual_jacobian with pinned host buffers; per rank its own shard. The d/dx_k block is "
@@ -362,6 +365,9 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(p, Z)
+        if world > 1:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     for ptr in (pZ, pD, pV):
         lib.pb2_host_free(ptr)

@@ -118,11 +118,13 @@ int pb2_residual_jacobian_async(pb2_handle* h, const double* dZ, double* ddelta,
                                 void* stream);
 int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu, double* dvals,
                               void* stream);
-/* Sharded (multi-GPU) use: the d/dx_k block of a unitary knot is I (x) E, n_b copies of one b x b
- * block, so what has to cross NVLink per knot is a COMPACT record [E (b*b) | jets, d/d dt, ones
- * ((m+2) n_x) | delta (n_x)] of pb2_compact_stride() doubles (0: this handle cannot produce it).
- * Each rank writes its records, one all-gather moves them, and pb2_expand_compact_async turns any
- * number of gathered records into the canonical delta / value arrays (pb2_structure_jac order). */
+/* Sharded (multi-GPU) use: the d/dx_k block of a unitary knot is I (x) E -- n_b copies of one b x b
+ * block whose second half of columns mirrors the first (E = [[P,-Q],[Q,P]]) -- and the d/dx_{k+1}
+ * entries are constant, so what has to cross NVLink (or PCIe) per knot is a COMPACT record
+ * [E columns 0..b/2-1 (b*b/2) | jets, d/d dt ((m+1) n_x) | delta (n_x)] of pb2_compact_stride()
+ * doubles (0: this handle cannot produce it).  Each rank writes its records, one all-gather moves
+ * them, and pb2_expand_compact_async turns any number of gathered records into the canonical delta /
+ * value arrays (pb2_structure_jac order). */
 int64_t pb2_compact_stride(const pb2_handle* h);
 int pb2_residual_jacobian_compact_async(pb2_handle* h, const double* dZ, double* dcompact, void* stream);
 int pb2_expand_compact_async(pb2_handle* h, const double* dcompact, int64_t n_knots, double* ddelta,

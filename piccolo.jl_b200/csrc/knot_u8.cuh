@@ -32,8 +32,7 @@ struct U8Params {
   int gw;                // warps per group: producer + (E,X) + ceil(m/2) jet warps
   int stagger;           // cycles by which a group with fewer knots than group 0 delays its start
   int stagger_g;         // additional delay of group g: g * stagger_g cycles
-  int compact;           // 1: [E once | jets, d/d dt, ones | delta] records of cstride doubles go to `jac`;
-                         // 2: host records [E columns 0..7 | jets, d/d dt | delta]
+  int compact;           // 1: records [E columns 0..7 | jets, d/d dt | delta] of cstride doubles go to `jac`
   int cstride;
   int dry;               // debug: 1 = exit after the prologue, 2 = exit immediately (launch-floor measurement)
   // shared-memory layout in doubles (u8_layout)
@@ -316,18 +315,13 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (p.compact == 2) {
-            // host record = [E columns 0..7 (128) | jets, d/d dt | delta]: the least that has to cross
-            // PCIe (the other half of E is its mirror image, the identity entries are constant)
+          if (p.compact) {
+            // record = [E columns 0..7 (128) | jets, d/d dt | delta]: the least that has to cross
+            // NVLink / PCIe (the other half of E is its mirror image, the identity entries are constant)
             double* rec = p.jac + (size_t)kprev * p.cstride;
             bulk_s2g(rec, a_stage, 1024u);
             bulk_s2g(rec + 128, a_stage + o_J, (uint32_t)(m + 1) * 1024u);
             bulk_s2g(rec + 128 + (m + 1) * 128, a_stage + o_D, 1024u);
-          } else if (p.compact) {
-            // record = [E (256) | jets, d/d dt, ones | delta]: what crosses NVLink in a sharded run
-            double* rec = p.jac + (size_t)kprev * p.cstride;
-            bulk_s2g(rec, a_stage, 2048u);
-            bulk_s2g(rec + 256, a_stage + o_J, (uint32_t)(m + 3) * 1024u);
           } else {
             bulk_s2g(p.jac + (size_t)kprev * p.nnz_jac, a_stage, (uint32_t)p.nnz_jac * 8u);
             if (p.delta) bulk_s2g(p.delta + (size_t)kprev * 128, a_stage + o_D, 1024u);
@@ -569,23 +563,28 @@ inline size_t u8_layout(U8Params& q, int gpc) {
   return sizeof(double) * ((size_t)q.o_grp + (size_t)gpc * q.grp_stride);
 }
 
-// Compact records -> canonical arrays: [E | J | delta] per knot becomes n_b copies of E, J, and delta.
-// Pure data movement (HBM-bound); one CTA per knot, grid-stride.
+// Compact records -> canonical arrays.  Record = [E columns 0..7 (128) | jets, d/d dt ((m+1) 128) |
+// delta (128)]: the propagator block is rebuilt from its first half (-E = -[[P,-Q],[Q,P]]), written
+// n_b = 8 times, and the constant identity entries are filled in.  Pure data movement (HBM-bound);
+// one CTA per knot, grid-stride.
 __global__ void __launch_bounds__(256) expand_compact_kernel(const double* __restrict__ comp, long long n_knots,
-                                                             int cstride, int bb, int n_b, int nJ, int n_x,
-                                                             int nnz_jac, double* __restrict__ delta,
-                                                             double* __restrict__ jac) {
+                                                             int cstride, int nJd, int nnz_jac,
+                                                             double* __restrict__ delta, double* __restrict__ jac) {
   for (long long r = blockIdx.x; r < n_knots; r += gridDim.x) {
     const double* src = comp + r * cstride;
     double* out = jac + r * nnz_jac;
-    for (int e = threadIdx.x; e < bb; e += blockDim.x) {
-      const double v = src[e];
-      for (int c = 0; c < n_b; ++c) out[(size_t)c * bb + e] = v;
+    {
+      const int e = threadIdx.x, col = e >> 4, row = e & 15;   // 256 threads <-> the 16 x 16 block
+      double v;
+      if (col < 8) v = src[e];
+      else v = row < 8 ? -src[(col - 8) * 16 + 8 + row] : src[(col - 8) * 16 + row - 8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) out[c * 256 + e] = v;
     }
-    out += (size_t)n_b * bb;
-    for (int e = threadIdx.x; e < nJ; e += blockDim.x) out[e] = src[bb + e];
-    if (delta)
-      for (int e = threadIdx.x; e < n_x; e += blockDim.x) delta[r * n_x + e] = src[bb + nJ + e];
+    out += 2048;
+    for (int e = threadIdx.x; e < nJd; e += blockDim.x) out[e] = src[128 + e];
+    if (threadIdx.x < 128) out[nJd + threadIdx.x] = 1.0;
+    if (delta && threadIdx.x < 128) delta[r * 128 + threadIdx.x] = src[128 + nJd + threadIdx.x];
   }
 }
 

@@ -146,7 +146,7 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.stagger = h->stagger;
     q.stagger_g = h->stagger_g;
     q.compact = compact;
-    q.cstride = compact == 2 ? (p.m + 3) * 128 : 256 + (p.m + 3) * 128;
+    q.cstride = (p.m + 3) * 128;
     if (const char* env = std::getenv("PB2_DRY")) q.dry = std::atoi(env);
     q.tables = h->dTables; q.ell = h->dEll;
     q.Z = dZ; q.delta = ddelta; q.jac = djac; q.trace = h->dTrace2;
@@ -575,7 +575,7 @@ int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu
 
 int64_t pb2_compact_stride(const pb2_handle* h) {
   if (!h || !(h->alg == PB2_ALG_DMMA && h->u8_ok) || (h->d.D % 2) || (h->d.x_off % 2)) return 0;
-  return 256 + (int64_t)(h->d.m + 3) * 128;
+  return (int64_t)(h->d.m + 3) * 128;
 }
 
 int pb2_residual_jacobian_compact_async(pb2_handle* h, const double* dZ, double* dcompact, void* stream) {
@@ -594,11 +594,10 @@ int pb2_expand_compact_async(pb2_handle* h, const double* dcompact, int64_t n_kn
   if (cs == 0) return fail(PB2_EINVAL, "pb2_expand_compact_async: unsupported for this handle");
   if (n_knots == 0) return PB2_OK;
   PB2_CUDA(cudaSetDevice(h->d.device));
-  const int bb = h->d.b * h->d.b, n_x = h->n_x();
+  const int n_x = h->n_x();
   const int blocks = (int)std::min<int64_t>(n_knots, (int64_t)h->n_sm * 8);
-  pb2::expand_compact_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dcompact, n_knots, (int)cs, bb, h->d.n_b,
-                                                                     (h->d.m + 2) * n_x, n_x, h->nnz_jac_knot(),
-                                                                     ddelta, dvals);
+  pb2::expand_compact_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dcompact, n_knots, (int)cs, (h->d.m + 1) * n_x,
+                                                                     h->nnz_jac_knot(), ddelta, dvals);
   PB2_CUDA(cudaGetLastError());
   h->launches++;
   return PB2_OK;
@@ -638,12 +637,12 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
     // record (9.2 KB instead of 23.5 KB per knot at C3) crosses PCIe; it lands in pinned memory in
     // chunks, and host threads replicate each chunk into the caller's arrays (pb2_structure_jac
     // order) while the next chunk is still in flight.  Data movement only.
-    const int64_t nk = h->nk(), cs = (int64_t)(h->d.m + 3) * 128;   // host record: [E cols 0..7 | jets, d/d dt | delta]
+    const int64_t nk = h->nk(), cs = pb2_compact_stride(h);   // record: [E cols 0..7 | jets, d/d dt | delta]
     const int n_x = h->n_x(), bb = h->d.b * h->d.b, n_b = h->d.n_b, nJd = (h->d.m + 1) * n_x, nnz = h->nnz_jac_knot();
     if ((rc = ensure(&h->dZ, &h->hZ, nZ))) return rc;
     if ((rc = ensure(&h->dComp, &h->hComp, (size_t)(nk * cs)))) return rc;
     if ((rc = stage_in(h, Z, h->hZ, h->dZ, nZ))) return rc;
-    if ((rc = launch_resjac(h, h->dZ, nullptr, h->dComp, h->stream, 2))) return rc;
+    if ((rc = launch_resjac(h, h->dZ, nullptr, h->dComp, h->stream, 1))) return rc;
     const int nch_env = std::getenv("PB2_D2H_CHUNKS") ? std::atoi(std::getenv("PB2_D2H_CHUNKS")) : 8;
     const int nch = (int)std::min<int64_t>(std::min(16, std::max(1, nch_env)), std::max<int64_t>(1, nk / 32));
     const int64_t per = (nk + nch - 1) / nch;

@@ -378,7 +378,7 @@ def test_compact_records_expand_to_canonical_arrays():
     p, Z, mu = C.trajectory(3, 333)
     B = make(p, "dmma")
     cs = B.compact_stride
-    assert cs == 256 + (p.m + 3) * 128
+    assert cs == (p.m + 3) * 128
     d, v = B.residual_jacobian(Z)
     dZ = torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda()
     n = p.K - 1
