@@ -35,6 +35,31 @@ def algorithmic_bytes_per_eval(p):
     return 8 * ((p.n_x + p.m + 1) + (p.n_x + p.n_b * p.b * p.b + p.n_x * p.m + p.n_x))
 
 
+def fp64_tensor_work(p, Z):
+    """FLOPs the tensor-core kernels issue for one callback: per knot (48 M - 24) DMMA.8x8x4
+    (E, X tiles M steps; 4 jet tiles M - 1 steps; one more product for d/d dt) of 512 FLOP each,
+    with the per-knot Taylor degree M the kernel derives from |dt| (||G_0||_1 + sum |u_j| ||G_j||_1).
+    Only meaningful for the 3-qubit unitary shape (b = 16, n_b = 8, m = 4)."""
+    import math
+    if not (p.b == 16 and p.n_b == 8 and p.m == 4):
+        return None
+
+    def theta(q, tol=2.0 ** -53):
+        lo, hi = 0.0, q + 1.0
+        for _ in range(200):
+            th = 0.5 * (lo + hi)
+            lg = (q + 1) * math.log(th) - math.lgamma(q + 2) - math.log1p(-th / (q + 2))
+            lo, hi = (th, hi) if lg <= math.log(tol) else (lo, th)
+        return lo
+    th = np.array([theta(q) for q in range(1, 18)])
+    n0 = np.abs(p.G0).sum(0).max()
+    nj = np.array([np.abs(g).sum(0).max() for g in p.Gj])
+    u = Z[p.u_off:p.u_off + p.m, :-1]
+    nrm = np.abs(Z[p.dt_off, :-1]) * (n0 + (np.abs(u) * nj[:, None]).sum(0))
+    M = 1 + (th[None, :] < nrm[:, None]).sum(1)
+    return float(((48 * M - 24) * 512).sum()), float(M.mean())
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -350,6 +375,7 @@ def run_ours(args):
                          "frac": achieved / peak, "traffic": ncu_traffic(workload),
                          "kernel": f"knot resjac ({B.algorithm})", "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": bytes_launch, "peak_source": peak_src},
+            "fp64_tensor": None,
             "e2e": {"value": n_eval * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": 8 * p.D * p.K,
                     "d2h_bytes_per_step": 8 * B.compact_stride * n_eval if B.compact_stride else 8 * (B.dim + B.nnz_jac),
@@ -363,6 +389,14 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
+        work = fp64_tensor_work(p, Z)
+        if work is not None:
+            # the kernel sits at the FP64 ridge: co-report the tensor pipe.  Peak = DMMA rate
+            # measured on this pool's B200 with tools/fp64_peak.cu (profiles/r01_fp64_peak_b200.json).
+            tf = work[0] / (kern_ms * 1e-3) / 1e12
+            line["fp64_tensor"] = {"achieved": tf, "peak": 37.13, "unit": "TFLOP/s", "frac": tf / 37.13,
+                                   "mean_taylor_degree": work[1],
+                                   "flops_per_launch": work[0], "peak_source": "measured (profiles/r01_fp64_peak_b200.json)"}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(p, Z)
         if world > 1:
