@@ -34,6 +34,8 @@ struct U8Params {
   int stagger_g;         // additional delay of group g: g * stagger_g cycles
   int compact;           // 1: records [E columns 0..7 | jets, d/d dt | delta] of cstride doubles go to `jac`
   int cstride;
+  int direct_last;       // 1: a group's LAST knot leaves straight from the accumulator registers (st.global.v2):
+                         // shortens the kernel's tail; every other knot goes through the stage + bulk store
   int dry;               // debug: 1 = exit after the prologue, 2 = exit immediately (launch-floor measurement)
   // shared-memory layout in doubles (u8_layout)
   int o_norm, o_tab, o_grp, grp_stride, zpad, o_prep, o_y, o_stage, o_mbar;
@@ -64,6 +66,10 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
 template <int OFF>
 __device__ __forceinline__ void sts_f64x2(uint32_t addr, double2 v) {
   asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(addr), "n"(OFF), "d"(v.x), "d"(v.y) : "memory");
+}
+
+__device__ __forceinline__ void stg_f64x2(double* ptr, double a, double b) {
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(a), "d"(b) : "memory");
 }
 
 // byte offset of element i (row 8 (i>>1) + 2q + (i&1)) relative to the lane's (column, 2q) address
@@ -296,7 +302,8 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         if (lane == 0) mbar_arrive(mb_ready + 8 * (i & 1));
         U8_STAMP(2);
       }
-      if (i >= 1) {
+      const bool direct_prev = p.direct_last && (i - 1) == n_my - 1;   // that knot's warps stored it themselves
+      if (i >= 1 && !direct_prev) {
         // ---- finish knot i-1: replicate the propagator block, one bulk store per output --------
         const int kprev = gg + (i - 1) * TG;
         const int i_knot = i - 1;
@@ -338,7 +345,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
           bulk_g2s(a_grp + 8u * (uint32_t)(s * p.zpad), p.Z + (size_t)(gg + (i + 2) * TG) * p.D, zbytes,
                    mb_zfull + 8 * s);
         }
-        if (i >= 1) {
+        if (i >= 1 && !direct_prev) {
           bulk_wait_read0();        // the stage has been read: the compute warps may refill it
           mbar_arrive(mb_free);
           { const int i_knot = i - 1; U8_STAMP(6); }
@@ -430,6 +437,34 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         for (int i4 = 0; i4 < 4; ++i4) xn[i4] = lds_f64<0>(a_z + 8u * p.D + xl + U8_OFF(i4));
       }
       U8_STAMP(4);
+      if (p.direct_last && i == n_my - 1) {
+        // the group's last knot: results straight from the accumulator registers, 16-byte stores
+        const size_t kk = (size_t)(gg + i * TG);
+        double* jk = p.jac + kk * (size_t)(p.compact ? p.cstride : p.nnz_jac);
+        const int lc = g * 16 + 2 * q;
+        if (p.compact) {
+          stg_f64x2(jk + lc, -tE[0], -tE[1]);
+          stg_f64x2(jk + lc + 8, -tE[2], -tE[3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            // -E = -[[P, -Q], [Q, P]]: own column g, mirrored column g + 8
+            stg_f64x2(jk + c * 256 + lc, -tE[0], -tE[1]);
+            stg_f64x2(jk + c * 256 + lc + 8, -tE[2], -tE[3]);
+            stg_f64x2(jk + c * 256 + 128 + lc + 8, -tE[0], -tE[1]);
+            stg_f64x2(jk + c * 256 + 128 + lc, tE[2], tE[3]);
+          }
+        }
+        double* jj = jk + (p.compact ? 128 : 2048);
+        stg_f64x2(jj + m * 128 + lc, -dT[0][0], -dT[0][1]);
+        stg_f64x2(jj + m * 128 + lc + 8, -dT[1][0], -dT[1][1]);
+        if (want_delta) {
+          double* dd = (p.compact ? jj + (m + 1) * 128 : p.delta + kk * 128) + lc;
+          stg_f64x2(dd, xn[0] - tX[0], xn[1] - tX[1]);
+          stg_f64x2(dd + 8, xn[2] - tX[2], xn[3] - tX[3]);
+        }
+        break;
+      }
       mbar_wait(mb_free, (uint32_t)(i & 1));
       U8_STAMP(5);
       // -E = -[[P, -Q], [Q, P]]: own column g, mirrored column g + 8
@@ -531,6 +566,22 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         if (kq == 0) u8_step_jets<W, 0, false, false>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
       }
       U8_STAMP(4);
+      if (p.direct_last && i == n_my - 1) {
+        const size_t kk = (size_t)(gg + i * TG);
+        double* jj = p.jac + kk * (size_t)(p.compact ? p.cstride : p.nnz_jac) + (p.compact ? 128 : 2048);
+        const int lc = g * 16 + 2 * q;
+        stg_f64x2(jj + jd0 * 128 + lc, -t[0][0], -t[0][1]);
+        stg_f64x2(jj + jd0 * 128 + lc + 8, -t[0][2], -t[0][3]);
+        if (two) {
+          stg_f64x2(jj + jd1 * 128 + lc, -t[1][0], -t[1][1]);
+          stg_f64x2(jj + jd1 * 128 + lc + 8, -t[1][2], -t[1][3]);
+        }
+        if (jw == 0 && !p.compact) {   // the constant d/dx_{k+1} identity entries
+          stg_f64x2(jj + (m + 1) * 128 + 2 * lane, 1.0, 1.0);
+          stg_f64x2(jj + (m + 1) * 128 + 64 + 2 * lane, 1.0, 1.0);
+        }
+        break;
+      }
       mbar_wait(mb_free, (uint32_t)(i & 1));
       U8_STAMP(5);
       sts_f64<0>(oJ0, -t[0][0]);   sts_f64<8>(oJ0, -t[0][1]);

@@ -106,6 +106,7 @@ struct pb2_handle {
   int stagger = 5000;   // cycles; PB2_STAGGER overrides (0 = off)
   int pdl = 1;
   int stagger_g = 0;
+  int direct_last = 1;
   pb2::EllEntry* dEll = nullptr;
   // staging for host-pointer calls
   double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
@@ -146,6 +147,7 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.stagger = h->stagger;
     q.stagger_g = h->stagger_g;
     q.compact = compact;
+    q.direct_last = h->direct_last;
     q.cstride = (p.m + 3) * 128;
     if (const char* env = std::getenv("PB2_DRY")) q.dry = std::atoi(env);
     q.tables = h->dTables; q.ell = h->dEll;
@@ -427,6 +429,7 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     if (const char* env = std::getenv("PB2_STAGGER")) h->stagger = std::atoi(env);
     if (const char* env = std::getenv("PB2_PDL")) h->pdl = std::atoi(env);
     if (const char* env = std::getenv("PB2_STAGGER_G")) h->stagger_g = std::atoi(env);
+    if (const char* env = std::getenv("PB2_DIRECT_LAST")) h->direct_last = std::atoi(env);
     h->u8_ok = h->plan.iso && d.b == 16 && d.n_b == 8 && d.m >= 1 && d.m <= 6 && !std::getenv("PB2_NO_U8");
     if (h->u8_ok)
       PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8_kernel(h->plan.W), cudaFuncAttributeMaxDynamicSharedMemorySize,
