@@ -86,6 +86,48 @@ __device__ __forceinline__ void u8_mma(double (&d)[2][2], const double (&t)[4], 
   }
 }
 
+// G(u) = G0 + sum_j u_j G_j for this lane's 8 B-fragment slots (all loads first, then the arithmetic)
+template <bool LOWREG>
+__device__ __forceinline__ void u8_build_G(uint32_t a_z, uint32_t a_cG, int lane, int m, int u_off, double (&acc)[8]) {
+  if (LOWREG) {   // one drive at a time: a few registers, used once per group at start-up
+#pragma unroll
+    for (int s = 0; s < 8; ++s) acc[s] = lds_f64<0>(a_cG + 8u * (uint32_t)(s * 32 + lane));
+    for (int j = 0; j < m; ++j) {
+      const double u = lds_f64<0>(a_z + 8u * (uint32_t)(u_off + j));
+      const uint32_t a_gj = a_cG + 8u * (uint32_t)((1 + j) * 256 + lane);
+      double gvj[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) gvj[s] = lds_f64<0>(a_gj + 256u * s);
+#pragma unroll
+      for (int s = 0; s < 8; ++s) acc[s] = fma(u, gvj[s], acc[s]);
+    }
+    return;
+  }
+  double uj[6], gv[6][8];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) uj[j] = j < m ? lds_f64<0>(a_z + 8u * (uint32_t)(u_off + j)) : 0.0;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) acc[s] = lds_f64<0>(a_cG + 8u * (uint32_t)(s * 32 + lane));
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (j < m) {
+      const uint32_t a_gj = a_cG + 8u * (uint32_t)((1 + j) * 256 + lane);
+#pragma unroll
+      for (int s = 0; s < 8; ++s) gv[j][s] = lds_f64<0>(a_gj + 256u * s);
+    }
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+    if (j < m) {
+      if (j >= 4) {   // drives 5, 6: loaded late to bound register use
+        const uint32_t a_gj = a_cG + 8u * (uint32_t)((1 + j) * 256 + lane);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) gv[j][s] = lds_f64<0>(a_gj + 256u * s);
+      }
+#pragma unroll
+      for (int s = 0; s < 8; ++s) acc[s] = fma(uj[j], gv[j][s], acc[s]);
+    }
+}
+
 // ---- one Horner step of the (E, X) warp.  FIRST: first sub-step (B = unit columns for E) ------
 template <int PAR, bool FIRST>
 __device__ __forceinline__ void u8_step_ex(double (&tE)[4], double (&tX)[4], const double (&bE)[4],
@@ -229,44 +271,19 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         U8_STAMP(0);
         mbar_wait(mb_zfull + 8 * s3, (uint32_t)((i / 3) & 1));
         U8_STAMP(1);
-        // all shared-memory loads first (they are independent), then the arithmetic
-        double uj[6], nj[6], gv[6][8], acc[8];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          uj[j] = 0.0;
-          nj[j] = 0.0;
-          if (j < m) {
-            uj[j] = lds_f64<0>(a_z + 8u * (uint32_t)(p.u_off + j));
-            nj[j] = lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_norm + 1 + j));
-          }
-        }
+        // the first knot's G(u) is built by the compute warps themselves (they are idle anyway, and it
+        // takes the hand-over off the start-up path); from then on this warp runs ahead of them
         double dt = lds_f64<0>(a_z + 8u * p.dt_off);
         double nrm = lds_f64<0>(a_cG + 8u * p.o_norm);
+        for (int j = 0; j < m; ++j)
+          nrm = fma(fabs(lds_f64<0>(a_z + 8u * (uint32_t)(p.u_off + j))),
+                    lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_norm + 1 + j)), nrm);
+        if (i > 0) {
+          double acc[8];
+          u8_build_G<false>(a_z, a_cG, lane, m, p.u_off, acc);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) acc[s] = lds_f64<0>(a_cG + 8u * (uint32_t)(s * 32 + lane));
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < m) {
-            const uint32_t a_gj = a_cG + 8u * (uint32_t)((1 + j) * 256 + lane);
-#pragma unroll
-            for (int s = 0; s < 8; ++s) gv[j][s] = lds_f64<0>(a_gj + 256u * s);
-          }
+          for (int s = 0; s < 8; ++s) sts_f64<0>(a_p + 8u * (uint32_t)(s * 32 + lane), acc[s]);
         }
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-          if (j < m) {
-            if (j >= 4) {   // drives 5, 6: loaded late to bound register use
-              const uint32_t a_gj = a_cG + 8u * (uint32_t)((1 + j) * 256 + lane);
-#pragma unroll
-              for (int s = 0; s < 8; ++s) gv[j][s] = lds_f64<0>(a_gj + 256u * s);
-            }
-#pragma unroll
-            for (int s = 0; s < 8; ++s) acc[s] = fma(uj[j], gv[j][s], acc[s]);
-            nrm = fma(fabs(uj[j]), nj[j], nrm);
-          }
-        }
-#pragma unroll
-        for (int s = 0; s < 8; ++s) sts_f64<0>(a_p + 8u * (uint32_t)(s * 32 + lane), acc[s]);
         nrm *= fabs(dt);
         int n_sub = 1;
         double per = nrm;
@@ -361,6 +378,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
 
   // ================================= compute warps ==================================================
   const uint32_t lane_col = 8u * (uint32_t)(g * 16 + 2 * q);   // (column g, row 2q) inside a 16 x 8 block
+  const uint32_t a_z0 = a_grp;                                  // slab slot 0 holds the group's first knot
   if (role == 1) {
     // ---- tiles E (columns 0..7 of the propagator) and X (the 8 state columns) -------------------
     const int iE = (g == 2 * q) ? 0 : ((g == 2 * q + 1) ? 1 : -1);   // which element is the unit entry
@@ -375,13 +393,24 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
       const uint32_t a_c = a_p + 8u * 256u;
       const int i_knot = i;
       U8_STAMP(0);
+      double A[4][2];
+      if (i == 0) {
+        // first knot: build G(u) here while the producer derives the Taylor degree and coefficients
+        double acc[8];
+        mbar_wait(mb_tab, 0);
+        mbar_wait(mb_zfull, 0);
+        u8_build_G<true>(a_z0, a_cG, lane, m, p.u_off, acc);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) A[s >> 1][s & 1] = acc[s];
+      }
       mbar_wait(mb_ready + 8 * (i & 1), (uint32_t)((i >> 1) & 1));
       U8_STAMP(1);
-      double A[4][2];
+      if (i > 0) {
 #pragma unroll
-      for (int kt = 0; kt < 4; ++kt)
+        for (int kt = 0; kt < 4; ++kt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) A[kt][nt] = lds_f64<0>(a_p + 8u * (uint32_t)((kt * 2 + nt) * 32 + lane));
+          for (int nt = 0; nt < 2; ++nt) A[kt][nt] = lds_f64<0>(a_p + 8u * (uint32_t)((kt * 2 + nt) * 32 + lane));
+      }
       int M, n_sub;
       lds_v2u32(a_p + 8u * 276u, M, n_sub);
       double bX[4], tE[4], tX[4];
@@ -512,13 +541,24 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
       const uint32_t a_c = a_p + 8u * 256u;
       const int i_knot = i;
       U8_STAMP(0);
+      double A[4][2];
+      if (i == 0) {
+        // first knot: build G(u) here while the producer derives the Taylor degree and coefficients
+        double acc[8];
+        mbar_wait(mb_tab, 0);
+        mbar_wait(mb_zfull, 0);
+        u8_build_G<true>(a_z0, a_cG, lane, m, p.u_off, acc);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) A[s >> 1][s & 1] = acc[s];
+      }
       mbar_wait(mb_ready + 8 * (i & 1), (uint32_t)((i >> 1) & 1));
       U8_STAMP(1);
-      double A[4][2];
+      if (i > 0) {
 #pragma unroll
-      for (int kt = 0; kt < 4; ++kt)
+        for (int kt = 0; kt < 4; ++kt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) A[kt][nt] = lds_f64<0>(a_p + 8u * (uint32_t)((kt * 2 + nt) * 32 + lane));
+          for (int nt = 0; nt < 2; ++nt) A[kt][nt] = lds_f64<0>(a_p + 8u * (uint32_t)((kt * 2 + nt) * 32 + lane));
+      }
       int M, n_sub;
       lds_v2u32(a_p + 8u * 276u, M, n_sub);
       double t[2][4];
