@@ -149,7 +149,9 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.compact = compact;
     q.direct_last = h->direct_last;
     q.cstride = (p.m + 3) * 128;
-    if (const char* env = std::getenv("PB2_DRY")) q.dry = std::atoi(env);
+#ifdef PB2_TRACE
+    if (const char* env = std::getenv("PB2_DRY")) q.dry = std::atoi(env);   // launch-floor measurement (debug build only)
+#endif
     q.tables = h->dTables; q.ell = h->dEll;
     q.Z = dZ; q.delta = ddelta; q.jac = djac; q.trace = h->dTrace2;
     int maxg = std::min(pb2::kU8MaxGroups, pb2::kU8MaxThreads / (32 * q.gw));
