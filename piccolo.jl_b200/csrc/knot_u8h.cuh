@@ -36,6 +36,7 @@ struct U8hParams {
   const double* Z;
   const double* mu;
   double* hess;
+  long long* trace;      // debug build only
 };
 
 constexpr int kU8hXchBytes = 6 * 1024;   // exchange buffers per step parity: X, Mt, J_0..J_3 (1 KB each)
@@ -296,7 +297,10 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
     const uint32_t a_mu = a_z + 8u * p.zpad + lane_col;
     const uint32_t a_p = a_prep + 8u * (uint32_t)((i & 1) * kU8Prep);
     const uint32_t a_c = a_p + 8u * 256u;
+    const int i_knot = i;
+    U8_STAMP(0);
     mbar_wait(mb_ready + 8 * (i & 1), (uint32_t)((i >> 1) & 1));
+    U8_STAMP(1);
     double A[4][2];
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt)
@@ -318,6 +322,7 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
         base[a][i4] = v;
       }
     bar_sync(1, nthr);   // exchange buffers free (readers of the previous knot are done)
+    U8_STAMP(2);
     for (int sub = 0; sub < n_sub; ++sub) {
       const double cM = lds_f64<0>(a_c + 8u * (uint32_t)M);
 #pragma unroll
@@ -339,6 +344,7 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
     }
 
     // ---- final products and contractions ------------------------------------------------------------
+    U8_STAMP(3);
     // the state tile publishes Y = E X once more: (u_j, dt) needs G_j Y.  It goes into the buffer
     // half the last Horner step did NOT use (that one may still be read by slower warps).
     const uint32_t fo = (uint32_t)(M & 1) * (uint32_t)kU8hXchBytes;
@@ -393,7 +399,9 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
         for (int i4 = 0; i4 < 4; ++i4) outv[a][i4] = -t[a][i4];
       }
     }
+    U8_STAMP(4);
     mbar_wait(mb_free, (uint32_t)(i & 1));
+    U8_STAMP(5);
     // stage: [(x,u_j) m x 128 | (x,dt) 128 | (u_i,u_j) npair | (u_j,dt) m | (dt,dt)]
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
@@ -410,6 +418,7 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(mb_staged);
+    U8_STAMP(6);
     s3 = s3 == 2 ? 0 : s3 + 1;
   }
 }

@@ -229,7 +229,7 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
     q.ntiles = 2 + 2 * p.m + p.m * (p.m + 1) / 2;
     q.ncw = (q.ntiles + 1) / 2;
     q.tables = h->dTables; q.ell = h->dEll;
-    q.Z = dZ; q.mu = dmu; q.hess = dhess;
+    q.Z = dZ; q.mu = dmu; q.hess = dhess; q.trace = h->dTrace2;
     const size_t smem = pb2::u8h_layout(q);
     if (smem > kSmemLimit) return fail(PB2_EINVAL, "u8h hessian: knot column too large for the shared-memory staging");
     const int blocks = std::min(h->n_sm, q.nk);

@@ -11,8 +11,12 @@ from oracle import configs as C
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 p, Z, _ = C.trajectory(cfg, int(sys.argv[2]) if len(sys.argv) > 2 else None)
 B = pb.B200BilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off, dt_off=p.dt_off, u_off=p.u_off)
+mode = os.environ.get("TRACE_MODE", "resjac")
 for _ in range(3):
-    B.residual_jacobian(Z)
+    if mode == "hess":
+        B.hessian_values(Z, _)  if False else B.hessian_values(Z, np.random.default_rng(0).standard_normal(B.dim))
+    else:
+        B.residual_jacobian(Z)
 out = np.zeros(8 * 16 * 8, dtype=np.int64)
 lib = pb.load_library()
 lib.pb2_debug_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
