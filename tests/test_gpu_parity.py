@@ -511,3 +511,24 @@ def test_multi_ket_and_sampling_integrator_vectors():
                                 dt_off=2 * n_x, u_off=2 * n_x + 2)
         check_all(p, Zs, rng.standard_normal(p.dim), B)
         B.close()
+
+
+def test_u8_kernels_with_offset_state_block():
+    """A 3-qubit unitary state that is NOT the first component of the knot column (second member of a
+    sampling ensemble): slab offsets, compact records and the Hessian's mu slab all use x_off."""
+    import dataclasses
+    p0, Z0, _ = C.trajectory(3, 90)
+    rng = np.random.default_rng(21)
+    n_x = p0.n_x
+    Z = np.asfortranarray(np.vstack([0.1 * rng.standard_normal((n_x, p0.K)), Z0]))   # [other block | C3 column]
+    p = dataclasses.replace(p0, D=Z.shape[0], x_off=n_x, dt_off=p0.dt_off + n_x, u_off=p0.u_off + n_x)
+    mu = rng.standard_normal(p.dim)
+    B = make(p, "dmma")
+    check_all(p, Z, mu, B)
+    d, v = B.residual_jacobian(Z)
+    B0 = make(p0, "dmma")
+    d0, v0 = B0.residual_jacobian(Z0)
+    assert np.array_equal(d, d0) and np.array_equal(v, v0)          # same numbers as the un-shifted problem
+    assert np.array_equal(B.hessian_values(Z, mu), B0.hessian_values(Z0, mu))
+    B.close()
+    B0.close()

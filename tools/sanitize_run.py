@@ -1,11 +1,35 @@
-import numpy as np, sys
-sys.path.insert(0, "/root/repo")
+"""Small end-to-end exercise of every kernel for compute-sanitizer (memcheck / racecheck):
+  compute-sanitizer --tool memcheck python tools/sanitize_run.py"""
+import sys, os
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
 import piccolo_b200 as pb
 from oracle import configs as C
 from oracle import knot as KN
-for cfg, K in ((3, 700), (2, 60), (4, 50)):
+
+for cfg, K in ((3, 700), (2, 60), (4, 50), (1, 20)):
     p, Z, mu = C.trajectory(cfg, K)
     B = pb.B200BilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off, dt_off=p.dt_off, u_off=p.u_off)
-    d, v = B.residual_jacobian(Z)
-    print(cfg, B.algorithm, float(np.abs(d - KN.residual(p, Z)).max()) if K < 100 else "-")
+    d, v = B.residual_jacobian(Z)                 # host path (compact D2H + host un-pack for C3)
+    h = B.hessian_values(Z, mu)
+    d2 = np.empty(B.dim)
+    B.evaluate_(d2, Z)
+    dZ = torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda()
+    dd = torch.zeros(B.dim, dtype=torch.float64, device="cuda")
+    dv = torch.zeros(B.nnz_jac, dtype=torch.float64, device="cuda")
+    B.residual_jacobian_device(dZ, dd, dv, None)  # device path (canonical arrays, bulk stores)
+    if B.compact_stride:
+        comp = torch.zeros(B.compact_stride * (p.K - 1), dtype=torch.float64, device="cuda")
+        B.residual_jacobian_compact_device(dZ, comp, None)
+        B.expand_compact_device(comp, p.K - 1, dd, dv, None)
+    torch.cuda.synchronize()
+    ok = np.array_equal(dd.cpu().numpy(), d) and np.array_equal(dv.cpu().numpy(), v)
+    err = float(np.abs(d - KN.residual(p, Z)).max()) if K < 100 else float("nan")
+    print(cfg, B.algorithm, "device==host:", ok, "residual err vs oracle:", err)
     B.close()
+    traj = pb.NamedTrajectory.smooth_pulse_layout(Z, p.n_x, p.m, "x")
+    L = pb.B200KnotLinearConstraints(traj)
+    L.residual_jacobian(Z)
+    L.hessian_values(np.ones(L.dim))
+    L.close()
