@@ -225,6 +225,33 @@ def run_ours(args):
         if cs:
             comp_all.append(torch.empty(cs * n_eval * world, dtype=torch.float64, device=dev))
             comp_loc.append(comp_all[-1][rank * cs * n_eval:(rank + 1) * cs * n_eval])
+    # N > 1, fused exchange: every rank maps every other rank's gather buffers (symmetric memory over NVLink) and the
+    # kernel writes each finished knot's record into all of them; the only collective left is a barrier
+    peer_ptrs, symm_handles, fused = [], [], False
+    symm_barrier = os.environ.get("PB2_SYMM_BARRIER", "1") == "1"
+    if cs and os.environ.get("PB2_FUSED_XCHG", "1") != "0":
+        try:
+            lib0 = pb.load_library()
+            for r in range(world):
+                if r != rank:
+                    assert lib0.pb2_enable_peer_access(local, r) == 0, lib0.pb2_last_error().decode()
+            import torch.distributed._symmetric_memory as symm_mem
+            for s in range(nsets):
+                # re-home this set's gather buffer in symmetric memory (cuMem-mapped into every rank)
+                t = symm_mem.empty(comp_all[s].numel(), dtype=torch.float64, device=dev)
+                hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+                comp_all[s] = t
+                comp_loc[s] = t[rank * cs * n_eval:(rank + 1) * cs * n_eval]
+                peer_ptrs.append([int(x) for x in hdl.buffer_ptrs])
+                symm_handles.append(hdl)
+            fused = True
+        except Exception as e:   # no peer mapping available: the NCCL all-gather path below is used
+            print(f"[bench] fused exchange unavailable ({e!r}); using NCCL all-gather", file=sys.stderr)
+            fused = False
+        flags = torch.tensor([1 if fused else 0], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        fused = bool(flags.item())
+    sync_token = torch.zeros(1, device=dev)
     # a dedicated non-default stream: the kernels, the timing events and (N > 1) the collective
     # all go on it, so the CUDA events bracket exactly the work they claim to
     stream = torch.cuda.Stream(device=dev)
@@ -234,6 +261,15 @@ def run_ours(args):
     def step(i, cuda_stream, collective=True):
         s = i % nsets
         if cs:
+            if collective and fused:
+                B.residual_jacobian_exchange_device(Zs[s], rank, peer_ptrs[s], rank * cs * n_eval, cuda_stream)
+                if symm_barrier:
+                    symm_handles[0].barrier(channel=0)   # signal-pad barrier of the symmetric-memory handle
+                else:
+                    dist.all_reduce(sync_token)      # barrier: every rank's records have landed everywhere
+                B.expand_compact_device(comp_all[s], n_eval * world, outs[s][:B.dim * world], outs[s][B.dim * world:],
+                                        cuda_stream)
+                return
             B.residual_jacobian_compact_device(Zs[s], comp_loc[s], cuda_stream)
             if collective:
                 dist.all_gather_into_tensor(comp_all[s], comp_loc[s])
@@ -265,6 +301,24 @@ def run_ours(args):
     for i in range(warmup):
         step(i, stream.cuda_stream)
     barrier()
+    if world > 1:
+        # self-check of the exchange (outside the timed region): buffer set 0 holds the same trajectory on
+        # every rank, so after a step each rank's shard of the gathered arrays must equal the local result
+        step(0, stream.cuda_stream)
+        barrier()
+        ref = torch.empty(chunk, dtype=torch.float64, device=dev)
+        B.residual_jacobian_device(Zs[0], ref[:B.dim], ref[B.dim:], stream.cuda_stream)
+        torch.cuda.synchronize()
+        got = outs[0]
+        for r in range(world):
+            if cs:
+                ok = torch.equal(got[r * B.dim:(r + 1) * B.dim], ref[:B.dim]) and \
+                     torch.equal(got[B.dim * world + r * B.nnz_jac:B.dim * world + (r + 1) * B.nnz_jac], ref[B.dim:])
+            else:
+                ok = torch.equal(got[r * chunk:(r + 1) * chunk], ref)
+            if not ok:
+                raise SystemExit(f"bench.py: rank {rank}: gathered shard of rank {r} differs from the local result")
+        barrier()
     l0 = B.launch_count
     g_step = capture(True)
     g_kern = capture(False) if world > 1 else g_step
@@ -368,7 +422,11 @@ def run_ours(args):
                               "inputs and outputs resident in HBM",
                            timing=f"the {args.steps} steps are captured once as a CUDA graph and replayed; CUDA events "
                                   f"around the replay, median of {reps} replays, max over ranks",
-                           collective=("one NCCL all_gather_into_tensor of the compact per-knot records "
+                           collective=("fused exchange: the kernel bulk-stores each knot's compact record "
+                                       f"({8 * cs} B instead of {8 * (p.n_x + p.nnz_jac_knot)} B) into every rank's gather buffer "
+                                       "over NVLink (torch symmetric memory), then one barrier (1-element all_reduce) and a local "
+                                       "expansion kernel" if (cs and fused) else
+                                       "one NCCL all_gather_into_tensor of the compact per-knot records "
                                        f"({8 * cs} B/knot instead of {8 * (p.n_x + p.nnz_jac_knot)} B), then a local expansion kernel" if cs
                                        else "one NCCL all_gather_into_tensor of [delta|vals] per step") if world > 1 else "none"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -129,6 +129,17 @@ int64_t pb2_compact_stride(const pb2_handle* h);
 int pb2_residual_jacobian_compact_async(pb2_handle* h, const double* dZ, double* dcompact, void* stream);
 int pb2_expand_compact_async(pb2_handle* h, const double* dcompact, int64_t n_knots, double* ddelta,
                              double* dvals, void* stream);
+/* Fused compute + exchange for sharded runs on one NVSwitch domain: gather_bufs[r] is rank r's gather
+ * buffer (of every rank's compact records) mapped into THIS process (CUDA IPC / symmetric memory;
+ * gather_bufs[rank] is the local one).  The kernel writes each finished knot's record into all
+ * n_ranks buffers at slot_offset (+ knot * stride) doubles -- bulk stores over NVLink that overlap the
+ * math of the following knots -- so no separate all-gather runs; the caller only needs a barrier
+ * across ranks before expanding / reading. */
+int pb2_residual_jacobian_exchange_async(pb2_handle* h, const double* dZ, int32_t n_ranks, int32_t rank,
+                                         double* const* gather_bufs, int64_t slot_offset, void* stream);
+/* cudaDeviceEnablePeerAccess(device -> peer) (idempotent); needed once before kernels on `device`
+ * write into memory that lives on `peer` */
+int pb2_enable_peer_access(int32_t device, int32_t peer);
 void* pb2_stream(const pb2_handle* h);
 int pb2_sync(pb2_handle* h);
 

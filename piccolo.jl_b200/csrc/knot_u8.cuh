@@ -34,6 +34,11 @@ struct U8Params {
   int stagger_g;         // additional delay of group g: g * stagger_g cycles
   int compact;           // 1: records [E columns 0..7 | jets, d/d dt | delta] of cstride doubles go to `jac`
   int cstride;
+  int n_peers;           // > 0 (sharded run): every record is written into each of peers[0..n_peers-1] (this
+                         // rank's gather buffer and, over NVLink, every other rank's) at p.jac's slot offset
+  double* peers[8];
+  int self;              // this rank's index in peers[]
+  int peer_tma;          // 1: peers are written with bulk (TMA) stores too (needs cuMem-mapped peer memory)
   int direct_last;       // 1: a group's LAST knot leaves straight from the accumulator registers (st.global.v2):
                          // shortens the kernel's tail; every other knot goes through the stage + bulk store
   int dry;               // debug: 1 = exit after the prologue, 2 = exit immediately (launch-floor measurement)
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         if (lane == 0) mbar_arrive(mb_ready + 8 * (i & 1));
         U8_STAMP(2);
       }
-      const bool direct_prev = p.direct_last && (i - 1) == n_my - 1;   // that knot's warps stored it themselves
+      const bool direct_prev = p.direct_last && p.n_peers == 0 && (i - 1) == n_my - 1;   // that knot's warps stored it themselves
       if (i >= 1 && !direct_prev) {
         // ---- finish knot i-1: replicate the propagator block, one bulk store per output --------
         const int kprev = gg + (i - 1) * TG;
@@ -336,16 +341,33 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) sts_f64x2<0>(a_stage + 2048u * c + 16u * (uint32_t)(lane + 32 * jj), v[jj]);
         }
+        if (p.n_peers > 1 && !p.peer_tma) {
+          // fused exchange: the record also goes straight into every other rank's gather buffer over
+          // NVLink.  Bulk (TMA) stores fault on CUDA-IPC peer mappings, so these are 16-byte st.global
+          // by this warp, read from the stage; they overlap the compute warps' next knot.
+          const uint32_t a_rec = a_stage + o_J - 1024u;
+          const size_t off = (size_t)(p.jac - p.peers[p.self]) + (size_t)kprev * p.cstride;
+          for (int e = lane; e < p.cstride / 2; e += 32) {
+            const double2 v2 = lds_f64x2<0>(a_rec + 16u * (uint32_t)e);
+            for (int r = 0; r < p.n_peers; ++r)
+              if (r != p.self) stg_f64x2(p.peers[r] + off + 2 * e, v2.x, v2.y);
+          }
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
           if (p.compact) {
             // record = [E columns 0..7 (128) | jets, d/d dt | delta]: the least that has to cross
-            // NVLink / PCIe (the other half of E is its mirror image, the identity entries are constant)
-            double* rec = p.jac + (size_t)kprev * p.cstride;
-            bulk_s2g(rec, a_stage, 1024u);
-            bulk_s2g(rec + 128, a_stage + o_J, (uint32_t)(m + 1) * 1024u);
-            bulk_s2g(rec + 128 + (m + 1) * 128, a_stage + o_D, 1024u);
+            // NVLink / PCIe (the other half of E is its mirror image, the identity entries are constant).
+            // In this mode the compute warps stage it contiguously (E half right below the jets, delta in
+            // the slot of the identity entries), so it leaves with one bulk store per destination.
+            const uint32_t a_rec = a_stage + o_J - 1024u, nbytes = (uint32_t)p.cstride * 8u;
+            bulk_s2g(p.jac + (size_t)kprev * p.cstride, a_rec, nbytes);
+            if (p.n_peers > 1 && p.peer_tma) {
+              const size_t off = (size_t)(p.jac - p.peers[p.self]) + (size_t)kprev * p.cstride;
+              for (int r = 0; r < p.n_peers; ++r)
+                if (r != p.self) bulk_s2g(p.peers[r] + off, a_rec, nbytes);
+            }
           } else {
             bulk_s2g(p.jac + (size_t)kprev * p.nnz_jac, a_stage, (uint32_t)p.nnz_jac * 8u);
             if (p.delta) bulk_s2g(p.delta + (size_t)kprev * 128, a_stage + o_D, 1024u);
@@ -372,7 +394,11 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
       s3 = s3 == 2 ? 0 : s3 + 1;
     }
     // the stage must outlive the bulk stores' reads of it; their writes complete with the grid
-    if (lane == 0) bulk_wait_read0();
+    if (p.n_peers > 1) __threadfence_system();   // remote writes are performed before the grid completes
+    if (lane == 0) {
+      if (p.n_peers > 1 && p.peer_tma) bulk_wait0();
+      else bulk_wait_read0();
+    }
     return;
   }
 
@@ -466,7 +492,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         for (int i4 = 0; i4 < 4; ++i4) xn[i4] = lds_f64<0>(a_z + 8u * p.D + xl + U8_OFF(i4));
       }
       U8_STAMP(4);
-      if (p.direct_last && i == n_my - 1) {
+      if (p.direct_last && p.n_peers == 0 && i == n_my - 1) {
         // the group's last knot: results straight from the accumulator registers, 16-byte stores
         const size_t kk = (size_t)(gg + i * TG);
         double* jk = p.jac + kk * (size_t)(p.compact ? p.cstride : p.nnz_jac);
@@ -496,12 +522,21 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
       }
       mbar_wait(mb_free, (uint32_t)(i & 1));
       U8_STAMP(5);
-      // -E = -[[P, -Q], [Q, P]]: own column g, mirrored column g + 8
-      sts_f64<0>(oE1, -tE[0]);   sts_f64<8>(oE1, -tE[1]);   sts_f64<64>(oE1, -tE[2]);  sts_f64<72>(oE1, -tE[3]);
-      sts_f64<64>(oE2, -tE[0]);  sts_f64<72>(oE2, -tE[1]);  sts_f64<0>(oE2, tE[2]);    sts_f64<8>(oE2, tE[3]);
-      if (want_delta) {
-        sts_f64<0>(oD, xn[0] - tX[0]);   sts_f64<8>(oD, xn[1] - tX[1]);
-        sts_f64<64>(oD, xn[2] - tX[2]);  sts_f64<72>(oD, xn[3] - tX[3]);
+      if (p.compact) {
+        // contiguous record [E columns 0..7 | jets | d/d dt | delta]: E half right below the jets, delta
+        // where the identity entries live in the canonical layout
+        const uint32_t oEc = a_stage + o_J - 1024u + lane_col, oDc = a_stage + o_J + 8u * (uint32_t)((m + 1) * 128) + lane_col;
+        sts_f64<0>(oEc, -tE[0]);   sts_f64<8>(oEc, -tE[1]);   sts_f64<64>(oEc, -tE[2]);  sts_f64<72>(oEc, -tE[3]);
+        sts_f64<0>(oDc, xn[0] - tX[0]);   sts_f64<8>(oDc, xn[1] - tX[1]);
+        sts_f64<64>(oDc, xn[2] - tX[2]);  sts_f64<72>(oDc, xn[3] - tX[3]);
+      } else {
+        // -E = -[[P, -Q], [Q, P]]: own column g, mirrored column g + 8
+        sts_f64<0>(oE1, -tE[0]);   sts_f64<8>(oE1, -tE[1]);   sts_f64<64>(oE1, -tE[2]);  sts_f64<72>(oE1, -tE[3]);
+        sts_f64<64>(oE2, -tE[0]);  sts_f64<72>(oE2, -tE[1]);  sts_f64<0>(oE2, tE[2]);    sts_f64<8>(oE2, tE[3]);
+        if (want_delta) {
+          sts_f64<0>(oD, xn[0] - tX[0]);   sts_f64<8>(oD, xn[1] - tX[1]);
+          sts_f64<64>(oD, xn[2] - tX[2]);  sts_f64<72>(oD, xn[3] - tX[3]);
+        }
       }
       sts_f64<0>(oT, -dT[0][0]);   sts_f64<8>(oT, -dT[0][1]);
       sts_f64<64>(oT, -dT[1][0]);  sts_f64<72>(oT, -dT[1][1]);
@@ -606,7 +641,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         if (kq == 0) u8_step_jets<W, 0, false, false>(t, bJ, A, ev, yad, a_c, two, xbar, nx);
       }
       U8_STAMP(4);
-      if (p.direct_last && i == n_my - 1) {
+      if (p.direct_last && p.n_peers == 0 && i == n_my - 1) {
         const size_t kk = (size_t)(gg + i * TG);
         double* jj = p.jac + kk * (size_t)(p.compact ? p.cstride : p.nnz_jac) + (p.compact ? 128 : 2048);
         const int lc = g * 16 + 2 * q;

@@ -131,7 +131,8 @@ pb2::KnotParams make_params(const pb2_handle* h) {
   return p;
 }
 
-int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, int compact = 0) {
+int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, int compact = 0,
+                  int n_peers = 0, double* const* peers = nullptr, int self = 0) {
   if (h->nk() <= 0) return PB2_OK;
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.delta = ddelta; p.jac = djac;
@@ -147,6 +148,10 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.stagger = h->stagger;
     q.stagger_g = h->stagger_g;
     q.compact = compact;
+    q.n_peers = n_peers;
+    q.peer_tma = std::getenv("PB2_PEER_TMA") ? std::atoi(std::getenv("PB2_PEER_TMA")) : 1;   // 0: 16-byte st.global instead
+    q.self = self;
+    for (int r = 0; r < n_peers && r < 8; ++r) q.peers[r] = peers[r];
     q.direct_last = h->direct_last;
     q.cstride = (p.m + 3) * 128;
 #ifdef PB2_TRACE
@@ -589,6 +594,32 @@ int pb2_residual_jacobian_compact_async(pb2_handle* h, const double* dZ, double*
   if (pb2_compact_stride(h) == 0) return fail(PB2_EINVAL, "pb2_residual_jacobian_compact_async: unsupported for this handle");
   PB2_CUDA(cudaSetDevice(h->d.device));
   return launch_resjac(h, dZ, nullptr, dcompact, (cudaStream_t)stream, 1);
+}
+
+int pb2_residual_jacobian_exchange_async(pb2_handle* h, const double* dZ, int32_t n_ranks, int32_t rank,
+                                         double* const* gather_bufs, int64_t slot_offset, void* stream) {
+  if (check(h)) return PB2_EINVAL;
+  if (!dZ || !gather_bufs || n_ranks < 1 || n_ranks > 8 || rank < 0 || rank >= n_ranks || slot_offset < 0)
+    return fail(PB2_EINVAL, "pb2_residual_jacobian_exchange_async: bad argument");
+  if (pb2_compact_stride(h) == 0)
+    return fail(PB2_EINVAL, "pb2_residual_jacobian_exchange_async: unsupported for this handle");
+  for (int r = 0; r < n_ranks; ++r)
+    if (!gather_bufs[r] || ((uintptr_t)gather_bufs[r] % 16) != 0)
+      return fail(PB2_EINVAL, "pb2_residual_jacobian_exchange_async: gather buffers must be 16-byte aligned device pointers");
+  PB2_CUDA(cudaSetDevice(h->d.device));
+  return launch_resjac(h, dZ, nullptr, gather_bufs[rank] + slot_offset, (cudaStream_t)stream, 1, n_ranks, gather_bufs, rank);
+}
+
+int pb2_enable_peer_access(int32_t device, int32_t peer) {
+  PB2_CUDA(cudaSetDevice(device));
+  int can = 0;
+  PB2_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
+  if (!can) return fail(PB2_EINVAL, "pb2_enable_peer_access: no peer access between these devices");
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+    return fail(PB2_ECUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+  cudaGetLastError();
+  return PB2_OK;
 }
 
 int pb2_expand_compact_async(pb2_handle* h, const double* dcompact, int64_t n_knots, double* ddelta, double* dvals,
