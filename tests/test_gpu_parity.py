@@ -532,3 +532,20 @@ def test_u8_kernels_with_offset_state_block():
     assert np.array_equal(B.hessian_values(Z, mu), B0.hessian_values(Z0, mu))
     B.close()
     B0.close()
+
+
+def test_sharded_integrator_single_rank_uses_compact_records():
+    """The sharding host logic on a real device (world size 1): compact records, local expansion, unpack."""
+    p, Z, mu = C.trajectory(3, 61)
+    S = pb.ShardedBilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off, dt_off=p.dt_off,
+                                     u_off=p.u_off, rank=0, world=1, device=0)
+    assert S.cs == (p.m + 3) * 128
+    S.residual_jacobian(Z)
+    import torch
+    torch.cuda.synchronize()
+    d, v = S.unpack()
+    B = make(p)
+    d0, v0 = B.residual_jacobian(Z)
+    assert np.array_equal(d, d0) and np.array_equal(v, v0)
+    B.close()
+    S.local.close()
