@@ -134,6 +134,45 @@ function DirectTrajOpt.hessian_of_lagrangian!(vals::AbstractVector{Float64}, B::
     return nothing
 end
 
+# ---- DerivativeIntegrator(x, ẋ, traj): x_{k+1} - x_k - Δt_k ẋ_k  (smooth_pulse_problem.jl:267-275) -----
+# One pair per Julia object (DirectTrajOpt keeps one integrator per pair); pb2_aux_* can also evaluate all
+# pairs of a trajectory plus the time-consistency rows in a single launch.
+struct PB2AuxDesc
+    K::Int32; D::Int32; dt_off::Int32; t_off::Int32; global_dim::Int32; n_pairs::Int32
+    x_off::NTuple{8,Int32}; xdot_off::NTuple{8,Int32}; dim::NTuple{8,Int32}
+    device::Int32
+end
+
+mutable struct B200DerivativeIntegrator <: AbstractIntegrator
+    handle::Ptr{Cvoid}
+    x_name::Symbol
+    xdot_name::Symbol
+    dim::Int
+    function B200DerivativeIntegrator(x::Symbol, ẋ::Symbol, traj::NamedTrajectory; device = 0)
+        comps = traj.components
+        pad(v) = ntuple(i -> i == 1 ? Int32(v) : Int32(0), 8)
+        desc = PB2AuxDesc(traj.N, traj.dim, first(comps[traj.timestep]) - 1, -1, traj.global_dim, 1,
+                          pad(first(comps[x]) - 1), pad(first(comps[ẋ]) - 1), pad(length(comps[x])), device)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:pb2_aux_create, LIB), Cint, (Ref{PB2AuxDesc}, Ref{Ptr{Cvoid}}), desc, h))
+        B = new(h[], x, ẋ, ccall((:pb2_aux_dim, LIB), Int64, (Ptr{Cvoid},), h[]))
+        finalizer(B -> ccall((:pb2_aux_destroy, LIB), Cvoid, (Ptr{Cvoid},), B.handle), B)
+        return B
+    end
+end
+
+function DirectTrajOpt.evaluate!(δ::AbstractVector{Float64}, B::B200DerivativeIntegrator, traj::NamedTrajectory)
+    check(ccall((:pb2_aux_residual_jacobian, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                B.handle, traj.datavec, δ, C_NULL, PB2_HOST))
+    return nothing
+end
+
+function DirectTrajOpt.jacobian!(vals::AbstractVector{Float64}, B::B200DerivativeIntegrator, traj::NamedTrajectory)
+    check(ccall((:pb2_aux_residual_jacobian, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                B.handle, traj.datavec, C_NULL, vals, PB2_HOST))
+    return nothing
+end
+
 # ---- registry hook: `integrator = "b200_bilinear"` in a ProblemSpec ---------------------------------
 # factory signature (qtraj, N; alg) -> integrator            src/specs/materialize.jl:216-222
 function __init__()

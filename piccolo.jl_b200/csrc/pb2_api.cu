@@ -487,6 +487,7 @@ void pb2_destroy(pb2_handle* h) {
   for (cudaEvent_t e : h->chunk_ev)
     if (e) cudaEventDestroy(e);
   if (h->dTrace) cudaFree(h->dTrace);
+  if (h->dTrace2) cudaFree(h->dTrace2);
   for (double* p : {h->hZ, h->hDelta, h->hJac, h->hMu, h->hHess})
     if (p) cudaFreeHost(p);
   if (h->stream) cudaStreamDestroy(h->stream);
