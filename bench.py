@@ -374,6 +374,42 @@ def run_ours(args):
                 else "knot_generic_kernel<2> (second-order Taylor jets in shared memory)"}
         del gh
 
+    # ---- objective value + gradient, device-resident, same graph scheme ----
+    objective = None
+    if world == 1 and p.kind == "unitary":
+        d = int(round(np.sqrt(p.n_x // 2)))
+        rng_o = np.random.default_rng(5)
+        Ug = np.linalg.qr(rng_o.standard_normal((d, d)) + 1j * rng_o.standard_normal((d, d)))[0]
+        comps = {"U": range(p.x_off, p.x_off + p.n_x), "Δt": range(p.dt_off, p.dt_off + 1),
+                 "u": range(p.u_off, p.u_off + p.m)}
+        traj = pb.NamedTrajectory(Z, comps)
+        Jobj = pb.UnitaryInfidelityObjective(Ug, "U", traj, Q=100.0) + pb.QuadraticRegularizer("u", traj, 1e-2)
+        dJ = torch.zeros(1, dtype=torch.float64, device=dev)
+        dG = [torch.empty(p.D * p.K, dtype=torch.float64, device=dev) for _ in range(2)]
+        osteps = max(3, min(args.steps, 200))
+        for i in range(3):
+            Jobj.value_gradient_device(Zs[i % nsets], dJ, dG[i & 1], stream.cuda_stream)
+        torch.cuda.synchronize()
+        go = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(go, stream=stream):
+            os_ = torch.cuda.current_stream().cuda_stream
+            for i in range(osteps):
+                Jobj.value_gradient_device(Zs[i % nsets], dJ, dG[i & 1], os_)
+        go.replay()
+        torch.cuda.synchronize()
+        ev[0].record()
+        go.replay()
+        ev[1].record()
+        torch.cuda.synchronize()
+        o_ms = ev[0].elapsed_time(ev[1]) / osteps
+        obytes = 16 * p.D * p.K
+        objective = {"ms_per_callback": o_ms, "terms": "UnitaryInfidelityObjective + QuadraticRegularizer(u)",
+                     "algorithmic_bytes": obytes, "achieved_GBps": obytes / (o_ms * 1e-3) / 1e9,
+                     "kernel": "knot_objective_kernel (one CTA per knot, one launch for value and gradient)",
+                     "note": "latency-bound at this size: the whole trajectory is %d KB" % (8 * p.D * p.K // 1024)}
+        del go
+        Jobj.close()
+
     # ---- end to end through the public host-pointer API (pinned host buffers, H2D + D2H) ----
     import ctypes
     lib = pb.load_library()
@@ -447,6 +483,7 @@ def run_ours(args):
                             "moves the non-redundant record per knot over PCIe in chunks and host threads replicate each "
                             "chunk into the caller's COO-ordered arrays while the next chunk is in flight"},
             "hessian": hess,
+            "objective": objective,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }

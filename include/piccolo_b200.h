@@ -176,6 +176,63 @@ int pb2_aux_residual_jacobian(pb2_aux* h, const double* Z, double* delta, double
 int pb2_aux_hess_lagrangian(pb2_aux* h, const double* mu, double* vals, int space);
 int pb2_aux_residual_jacobian_async(pb2_aux* h, const double* dZ, double* ddelta, double* dvals, void* stream);
 
+/* ---- objective value + gradient on the device-resident trajectory -------------
+ * J(Z) = sum of terms + sum of quadratic regularizers, with its dense gradient over the K*D
+ * trajectory entries (the caller appends zeros for global variables).  Replaces the eval_f /
+ * eval_grad_f callbacks DirectTrajOpt builds from the objectives Piccolo's templates assemble
+ * (src/control/templates/smooth_pulse_problem.jl:240-250).
+ *
+ * A term is a loss of one knot column z (restricted to `rows`), in real form
+ *     F = scale * ((a_re.z)^2 + (a_im.z)^2 + sum_i a_sq[i] z_i^2) + a_lin.z,
+ *     loss = Q*|1 - F|  (PB2_OBJ_ONE_MINUS)  or  Q*F,
+ * evaluated at the terminal knot (n_times = 0) or at `times` with weights Q[t].  It covers
+ *   KetInfidelityObjective              src/control/objectives.jl:24-38, 56-64   (a_re, a_im from the goal ket)
+ *   CoherentKetInfidelityObjective      :96-121, 181-216   (rows = all state blocks, weights folded into a_*)
+ *   UnitaryInfidelityObjective          :330-337, 347-356  (scale = 1/n^2)
+ *     ... with an EmbeddedOperator goal :339-345           (a_sq = subspace mask, scale = 1/(n(n+1)); unitary goal)
+ *   DensityMatrix[PureState]InfidelityObjective :387-394, 412-419  (a_lin; F is linear in the compact iso)
+ *   LeakageObjective                    :464-474           (a_sq = 1/len on the leakage rows, Q*F at `times`)
+ * The free-phase objectives (:283-324, :358-383) take a Julia closure over global variables and the
+ * quartic UnitarySensitivityObjective (:447-458) are not expressible here and stay in the reference.
+ * d|x|/dx is +1 at x = +0 (ForwardDiff's rule).
+ *
+ * A regularizer is  1/2 sum_{k in times} sum_i R[i] (z_k[rows[i]] - baseline[i,k])^2 dt_k^dt_power,
+ * dt_power in {0,1,2}.  DirectTrajOpt's QuadraticRegularizer source is not part of the reference tree
+ * and no reference test pins its value, so the power is the caller's to choose (parity unpinned). */
+#define PB2_OBJ_ONE_MINUS 1
+typedef struct pb2_obj_term {
+  int32_t flags;
+  int32_t n_rows;
+  const int32_t* rows;          /* 0-based rows of the knot column, distinct */
+  const double *a_re, *a_im, *a_sq, *a_lin;   /* n_rows each; NULL = all zero */
+  double scale;
+  int32_t n_times;              /* 0: the terminal knot, weight Q[0] */
+  const int32_t* times;         /* 0-based knots */
+  const double* Q;              /* max(n_times, 1) weights */
+} pb2_obj_term;
+typedef struct pb2_obj_reg {
+  int32_t n_rows;
+  const int32_t* rows;          /* distinct */
+  const double* R;              /* n_rows */
+  const double* baseline;       /* n_rows x K column-major, or NULL */
+  int32_t dt_power;
+  int32_t n_times;              /* 0: every knot */
+  const int32_t* times;
+} pb2_obj_reg;
+typedef struct pb2_obj_desc {
+  int32_t K, D, dt_off;
+  int32_t n_terms, n_regs;
+  const pb2_obj_term* terms;
+  const pb2_obj_reg* regs;
+  int32_t device;
+} pb2_obj_desc;
+typedef struct pb2_obj pb2_obj;
+int pb2_obj_create(const pb2_obj_desc* desc, pb2_obj** out);   /* copies everything it needs */
+void pb2_obj_destroy(pb2_obj* h);
+/* J -> *J; gradient (K*D doubles) -> grad unless NULL.  space = PB2_HOST or PB2_DEVICE for Z, J, grad */
+int pb2_obj_value_gradient(pb2_obj* h, const double* Z, double* J, double* grad, int space);
+int pb2_obj_value_gradient_async(pb2_obj* h, const double* dZ, double* dJ, double* dgrad, void* stream);
+
 /* pinned host memory for callers that want DMA without the staging copy */
 int pb2_host_alloc(void** ptr, int64_t bytes);
 int pb2_host_free(void* ptr);

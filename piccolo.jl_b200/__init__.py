@@ -10,6 +10,7 @@ integrator plug-in interface for this path only:
     eval_jacobian(B, traj)         integrators.jl:780-782             eval_jacobian(B, traj)
     jacobian_structure / hessian_structure   test/aqua.jl:6-9         same names
     B.dim, B.x_dim, B.x_name       integrators.jl:307-309,552         same fields
+    *InfidelityObjective, LeakageObjective, QuadraticRegularizer      objectives.py (src/control/objectives.jl)
 
 All arithmetic happens in libpiccolo_b200.so (hand-written sm_100a CUDA behind the C ABI of
 include/piccolo_b200.h).  There is no CPU fallback: importing works anywhere, but constructing an
@@ -24,6 +25,11 @@ from .integrators import (  # noqa: F401
     B200BilinearIntegrator, B200KnotLinearConstraints, BilinearIntegrator, DensityTrajectory, KetTrajectory,
     MultiKetTrajectory, NamedTrajectory, OpenQuantumSystem, QuantumSystem, SamplingTrajectory, UnitaryTrajectory,
     eval_jacobian, evaluate_, hessian_of_lagrangian, hessian_structure, jacobian_structure,
+)
+from .objectives import (  # noqa: F401
+    B200Objective, CoherentKetInfidelityObjective, DensityMatrixInfidelityObjective,
+    DensityMatrixPureStateInfidelityObjective, KetInfidelityObjective, LeakageObjective, QuadraticRegularizer,
+    UnitaryInfidelityObjective, gradient_, objective_value,
 )
 from .sharding import ShardedBilinearIntegrator, knot_partition  # noqa: F401
 

@@ -23,6 +23,7 @@ SYMBOLS = [
     "pb2_aux_create", "pb2_aux_destroy", "pb2_aux_dim", "pb2_aux_nnz_jac", "pb2_aux_nnz_hess",
     "pb2_aux_structure_jac", "pb2_aux_structure_hess", "pb2_aux_residual_jacobian", "pb2_aux_hess_lagrangian",
     "pb2_aux_residual_jacobian_async",
+    "pb2_obj_create", "pb2_obj_destroy", "pb2_obj_value_gradient", "pb2_obj_value_gradient_async",
     "pb2_stream", "pb2_sync", "pb2_host_alloc", "pb2_host_free", "pb2_launch_count",
 ]
 
@@ -53,6 +54,32 @@ class pb2_aux_desc(ctypes.Structure):
         ("global_dim", ctypes.c_int32), ("n_pairs", ctypes.c_int32),
         ("x_off", ctypes.c_int32 * PB2_AUX_MAX_PAIRS), ("xdot_off", ctypes.c_int32 * PB2_AUX_MAX_PAIRS),
         ("dim", ctypes.c_int32 * PB2_AUX_MAX_PAIRS), ("device", ctypes.c_int32),
+    ]
+
+
+class pb2_obj_term(ctypes.Structure):
+    _fields_ = [
+        ("flags", ctypes.c_int32), ("n_rows", ctypes.c_int32), ("rows", ctypes.POINTER(ctypes.c_int32)),
+        ("a_re", ctypes.POINTER(ctypes.c_double)), ("a_im", ctypes.POINTER(ctypes.c_double)),
+        ("a_sq", ctypes.POINTER(ctypes.c_double)), ("a_lin", ctypes.POINTER(ctypes.c_double)),
+        ("scale", ctypes.c_double), ("n_times", ctypes.c_int32), ("times", ctypes.POINTER(ctypes.c_int32)),
+        ("Q", ctypes.POINTER(ctypes.c_double)),
+    ]
+
+
+class pb2_obj_reg(ctypes.Structure):
+    _fields_ = [
+        ("n_rows", ctypes.c_int32), ("rows", ctypes.POINTER(ctypes.c_int32)), ("R", ctypes.POINTER(ctypes.c_double)),
+        ("baseline", ctypes.POINTER(ctypes.c_double)), ("dt_power", ctypes.c_int32), ("n_times", ctypes.c_int32),
+        ("times", ctypes.POINTER(ctypes.c_int32)),
+    ]
+
+
+class pb2_obj_desc(ctypes.Structure):
+    _fields_ = [
+        ("K", ctypes.c_int32), ("D", ctypes.c_int32), ("dt_off", ctypes.c_int32), ("n_terms", ctypes.c_int32),
+        ("n_regs", ctypes.c_int32), ("terms", ctypes.POINTER(pb2_obj_term)), ("regs", ctypes.POINTER(pb2_obj_reg)),
+        ("device", ctypes.c_int32),
     ]
 
 
@@ -114,6 +141,11 @@ def load_library():
     L.pb2_aux_residual_jacobian.argtypes = [H, vp, vp, vp, ctypes.c_int]
     L.pb2_aux_hess_lagrangian.argtypes = [H, vp, vp, ctypes.c_int]
     L.pb2_aux_residual_jacobian_async.argtypes = [H, vp, vp, vp, vp]
+    L.pb2_obj_create.argtypes = [ctypes.POINTER(pb2_obj_desc), ctypes.POINTER(H)]
+    L.pb2_obj_destroy.argtypes = [H]
+    L.pb2_obj_destroy.restype = None
+    L.pb2_obj_value_gradient.argtypes = [H, vp, vp, vp, ctypes.c_int]
+    L.pb2_obj_value_gradient_async.argtypes = [H, vp, vp, vp, vp]
     L.pb2_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_int64]
     L.pb2_host_free.argtypes = [vp]
     _lib = L

@@ -25,6 +25,7 @@
 #include "knot_u8.cuh"
 #include "knot_u8h.cuh"
 #include "knot_aux.cuh"
+#include "knot_objective.cuh"
 #include "host_pool.h"
 
 namespace {
@@ -971,6 +972,216 @@ int pb2_aux_hess_lagrangian(pb2_aux* h, const double* mu, double* vals, int spac
   PB2_CUDA(cudaGetLastError());
   PB2_CUDA(cudaMemcpyAsync(vals, h->dHess, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   PB2_CUDA(cudaStreamSynchronize(h->stream));
+  return PB2_OK;
+}
+
+// ---- objective value + gradient ---------------------------------------------------------------------
+struct pb2_obj {
+  int K = 0, D = 0, dt_off = 0, n_terms = 0, n_regs = 0, device = 0;
+  pb2::ObjParams p{};
+  cudaStream_t stream = nullptr;
+  std::vector<void*> owned;            // device allocations behind p
+  double *dZ = nullptr, *dGrad = nullptr, *dJ = nullptr;
+  double* hJ = nullptr;                // pinned
+  size_t smem = 0;
+};
+
+extern "C++" {
+template <class T>
+static int obj_upload(pb2_obj* h, const std::vector<T>& v, const T** out) {
+  void* d = nullptr;
+  PB2_CUDA(cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(T)));
+  h->owned.push_back(d);
+  if (!v.empty()) PB2_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = (const T*)d;
+  return PB2_OK;
+}
+}  // extern "C++"
+
+static int obj_build(pb2_obj* h, const pb2_obj_desc& d) {
+  const int K = d.K;
+  std::vector<int> t_off(1, 0), t_flags, rows, r_off(1, 0), r_pow, r_rows;
+  std::vector<double> t_scale, a_re, a_im, a_sq, a_lin, r_R, r_w((size_t)d.n_regs * K, 0.0);
+  std::vector<std::vector<std::pair<int, double>>> per_knot(K);
+  for (int t = 0; t < d.n_terms; ++t) {
+    const pb2_obj_term& T = d.terms[t];
+    for (int i = 0; i < T.n_rows; ++i) {
+      rows.push_back(T.rows[i]);
+      a_re.push_back(T.a_re ? T.a_re[i] : 0.0);
+      a_im.push_back(T.a_im ? T.a_im[i] : 0.0);
+      a_sq.push_back(T.a_sq ? T.a_sq[i] : 0.0);
+      a_lin.push_back(T.a_lin ? T.a_lin[i] : 0.0);
+    }
+    t_off.push_back((int)rows.size());
+    t_flags.push_back(T.flags);
+    t_scale.push_back(T.scale);
+    if (T.n_times == 0) per_knot[K - 1].push_back({t, T.Q[0]});
+    else
+      for (int i = 0; i < T.n_times; ++i) per_knot[T.times[i]].push_back({t, T.Q[i]});
+  }
+  std::vector<int> knot_ptr(1, 0), item_term;
+  std::vector<double> item_q;
+  for (int k = 0; k < K; ++k) {
+    for (auto& it : per_knot[k]) {
+      item_term.push_back(it.first);
+      item_q.push_back(it.second);
+    }
+    knot_ptr.push_back((int)item_term.size());
+  }
+  std::vector<const double*> r_base(std::max(d.n_regs, 1), nullptr);
+  for (int r = 0; r < d.n_regs; ++r) {
+    const pb2_obj_reg& R = d.regs[r];
+    for (int i = 0; i < R.n_rows; ++i) {
+      r_rows.push_back(R.rows[i]);
+      r_R.push_back(R.R[i]);
+    }
+    r_off.push_back((int)r_rows.size());
+    r_pow.push_back(R.dt_power);
+    if (R.n_times == 0) std::fill(r_w.begin() + (size_t)r * K, r_w.begin() + (size_t)(r + 1) * K, 1.0);
+    else
+      for (int i = 0; i < R.n_times; ++i) r_w[(size_t)r * K + R.times[i]] = 1.0;
+    if (R.baseline) {
+      std::vector<double> b(R.baseline, R.baseline + (size_t)R.n_rows * K);
+      int rc = obj_upload(h, b, &r_base[r]);
+      if (rc) return rc;
+    }
+  }
+  pb2::ObjParams& p = h->p;
+  p.K = K; p.D = d.D; p.dt_off = d.dt_off; p.n_regs = d.n_regs;
+  int rc;
+  if ((rc = obj_upload(h, knot_ptr, &p.knot_ptr)) || (rc = obj_upload(h, item_term, &p.item_term)) ||
+      (rc = obj_upload(h, item_q, &p.item_q)) || (rc = obj_upload(h, t_off, &p.t_off)) ||
+      (rc = obj_upload(h, t_flags, &p.t_flags)) || (rc = obj_upload(h, t_scale, &p.t_scale)) ||
+      (rc = obj_upload(h, rows, &p.rows)) || (rc = obj_upload(h, a_re, &p.a_re)) ||
+      (rc = obj_upload(h, a_im, &p.a_im)) || (rc = obj_upload(h, a_sq, &p.a_sq)) ||
+      (rc = obj_upload(h, a_lin, &p.a_lin)) || (rc = obj_upload(h, r_off, &p.r_off)) ||
+      (rc = obj_upload(h, r_pow, &p.r_pow)) || (rc = obj_upload(h, r_rows, &p.r_rows)) ||
+      (rc = obj_upload(h, r_R, &p.r_R)) || (rc = obj_upload(h, r_w, &p.r_w)))
+    return rc;
+  const double* const* dbase = nullptr;
+  if ((rc = obj_upload(h, r_base, (const double* const**)&dbase))) return rc;
+  p.r_base = dbase;
+  std::vector<double> zeros((size_t)K + 1, 0.0);
+  const double* jp = nullptr;
+  if ((rc = obj_upload(h, zeros, &jp))) return rc;
+  p.Jpart = const_cast<double*>(jp);
+  std::vector<unsigned int> cz(1, 0u);
+  const unsigned int* cp = nullptr;
+  if ((rc = obj_upload(h, cz, &cp))) return rc;
+  p.counter = const_cast<unsigned int*>(cp);
+  return PB2_OK;
+}
+
+int pb2_obj_create(const pb2_obj_desc* desc, pb2_obj** out) {
+  if (!desc || !out) return fail(PB2_EINVAL, "pb2_obj_create: null argument");
+  *out = nullptr;
+  const pb2_obj_desc& d = *desc;
+  if (d.K < 1 || d.D < 1 || d.n_terms < 0 || d.n_regs < 0 || (d.n_terms && !d.terms) || (d.n_regs && !d.regs))
+    return fail(PB2_EINVAL, "pb2_obj_create: bad sizes");
+  if (d.dt_off < 0 || d.dt_off >= d.D) return fail(PB2_EINVAL, "pb2_obj_create: timestep offset outside the knot column");
+  auto rows_ok = [&](const int32_t* rows, int n) {
+    if (n < 0 || (n && !rows)) return false;
+    std::vector<char> seen(d.D, 0);
+    for (int i = 0; i < n; ++i) {
+      if (rows[i] < 0 || rows[i] >= d.D || seen[rows[i]]) return false;
+      seen[rows[i]] = 1;
+    }
+    return true;
+  };
+  auto times_ok = [&](const int32_t* times, int n) {
+    if (n < 0 || (n && !times)) return false;
+    for (int i = 0; i < n; ++i)
+      if (times[i] < 0 || times[i] >= d.K) return false;
+    return true;
+  };
+  for (int t = 0; t < d.n_terms; ++t) {
+    const pb2_obj_term& T = d.terms[t];
+    if (!rows_ok(T.rows, T.n_rows) || !times_ok(T.times, T.n_times) || !T.Q)
+      return fail(PB2_EINVAL, "pb2_obj_create: term rows must be distinct and inside the knot column, times inside 0..K-1");
+  }
+  for (int r = 0; r < d.n_regs; ++r) {
+    const pb2_obj_reg& R = d.regs[r];
+    if (!rows_ok(R.rows, R.n_rows) || !times_ok(R.times, R.n_times) || (R.n_rows && !R.R) || R.dt_power < 0 ||
+        R.dt_power > 2)
+      return fail(PB2_EINVAL, "pb2_obj_create: regularizer rows / times / dt_power out of range");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(PB2_ENODEVICE, "pb2_obj_create: no CUDA device (this library has no CPU path)");
+  }
+  if (d.device < 0 || d.device >= ndev) return fail(PB2_EINVAL, "pb2_obj_create: bad device ordinal");
+  PB2_CUDA(cudaSetDevice(d.device));
+  pb2_obj* h = new (std::nothrow) pb2_obj();
+  if (!h) return fail(PB2_ENOMEM, "pb2_obj_create: out of memory");
+  h->K = d.K; h->D = d.D; h->dt_off = d.dt_off; h->n_terms = d.n_terms; h->n_regs = d.n_regs; h->device = d.device;
+  h->smem = 2 * (size_t)d.D * sizeof(double);
+  int rc = obj_build(h, d);
+  if (!rc && h->smem > 48 * 1024) {
+    if (h->smem > 200 * 1024) rc = fail(PB2_EINVAL, "pb2_obj_create: knot column too large for shared memory");
+    else if (cudaFuncSetAttribute(pb2::knot_objective_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)h->smem) != cudaSuccess)
+      rc = fail(PB2_ECUDA, "pb2_obj_create: cudaFuncSetAttribute failed");
+  }
+  if (!rc && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    rc = fail(PB2_ECUDA, "pb2_obj_create: cudaStreamCreate failed");
+  if (!rc && cudaMallocHost((void**)&h->hJ, sizeof(double)) != cudaSuccess)
+    rc = fail(PB2_ECUDA, "pb2_obj_create: cudaMallocHost failed");
+  if (rc) {
+    pb2_obj_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return PB2_OK;
+}
+
+void pb2_obj_destroy(pb2_obj* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (void* q : h->owned) cudaFree(q);
+  for (double* q : {h->dZ, h->dGrad, h->dJ})
+    if (q) cudaFree(q);
+  if (h->hJ) cudaFreeHost(h->hJ);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaGetLastError();
+  delete h;
+}
+
+static int obj_launch(pb2_obj* h, const double* dZ, double* dJ, double* dgrad, cudaStream_t st) {
+  pb2::ObjParams p = h->p;
+  p.Z = dZ; p.J = dJ; p.grad = dgrad;
+  pb2::knot_objective_kernel<<<h->K, pb2::kObjThreads, h->smem, st>>>(p);
+  PB2_CUDA(cudaGetLastError());
+  return PB2_OK;
+}
+
+int pb2_obj_value_gradient_async(pb2_obj* h, const double* dZ, double* dJ, double* dgrad, void* stream) {
+  if (!h || !dZ || !dJ) return fail(PB2_EINVAL, "pb2_obj_value_gradient_async: null argument");
+  PB2_CUDA(cudaSetDevice(h->device));
+  return obj_launch(h, dZ, dJ, dgrad, (cudaStream_t)stream);
+}
+
+int pb2_obj_value_gradient(pb2_obj* h, const double* Z, double* J, double* grad, int space) {
+  if (!h || !Z || !J) return fail(PB2_EINVAL, "pb2_obj_value_gradient: null argument");
+  PB2_CUDA(cudaSetDevice(h->device));
+  if (space == PB2_DEVICE) {
+    int rc = obj_launch(h, Z, J, grad, h->stream);
+    if (rc) return rc;
+    PB2_CUDA(cudaStreamSynchronize(h->stream));
+    return PB2_OK;
+  }
+  if (space != PB2_HOST) return fail(PB2_EINVAL, "pb2_obj_value_gradient: bad space");
+  const size_t nZ = (size_t)h->D * h->K;
+  int rc;
+  if ((rc = aux_ensure(&h->dZ, nZ)) || (rc = aux_ensure(&h->dJ, 1)) || (grad && (rc = aux_ensure(&h->dGrad, nZ))))
+    return rc;
+  PB2_CUDA(cudaMemcpyAsync(h->dZ, Z, nZ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = obj_launch(h, h->dZ, h->dJ, grad ? h->dGrad : nullptr, h->stream))) return rc;
+  PB2_CUDA(cudaMemcpyAsync(h->hJ, h->dJ, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (grad) PB2_CUDA(cudaMemcpyAsync(grad, h->dGrad, nZ * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PB2_CUDA(cudaStreamSynchronize(h->stream));
+  *J = *h->hJ;
   return PB2_OK;
 }
 

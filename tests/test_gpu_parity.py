@@ -549,3 +549,187 @@ def test_sharded_integrator_single_rank_uses_compact_records():
     assert np.array_equal(d, d0) and np.array_equal(v, v0)
     B.close()
     S.local.close()
+
+
+# ---- objective value + gradient --------------------------------------------------
+OBJ_RTOL = 1e-12      # relative to max(|J|, 1) and to max|grad|
+
+
+def _obj_check(J, Z, J_ref, g_ref):
+    val, g = J.value_gradient(Z)
+    assert abs(val - J_ref) < OBJ_RTOL * max(1.0, abs(J_ref))
+    assert g.shape == g_ref.shape
+    assert np.abs(g - g_ref).max() < OBJ_RTOL * max(1.0, np.abs(g_ref).max())
+    assert J.value(Z) == val                       # value-only entry point, bitwise the same sum
+    val2, g2 = J.value_gradient(Z)
+    assert val2 == val and np.array_equal(g, g2)   # deterministic (knot-ordered final sum)
+    return val, g
+
+
+def test_objectives_match_oracle_on_reference_solutions():
+    from oracle import objectives as OB
+    CX = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], complex)
+    p, Zg = GU.load("two_qubit_zoh")
+    rng = np.random.default_rng(21)
+    for Z in (Zg, np.asfortranarray(Zg + 0.05 * rng.standard_normal(Zg.shape))):
+        traj = pb.NamedTrajectory.smooth_pulse_layout(Z, p.n_x, p.m, "Ũ⃗")
+        # the objective SmoothPulseProblem assembles: infidelity + three regularizers (smooth_pulse_problem.jl:240-250)
+        J = pb.UnitaryInfidelityObjective(CX, "Ũ⃗", traj, Q=100.0)
+        Jo, go = OB.unitary_infidelity(Z[:p.n_x, -1], CX, 100.0)
+        G = np.zeros_like(Z)
+        G[:p.n_x, -1] = go
+        for pw, (name, R) in enumerate((("u", 1e-2), ("du", 2e-2), ("ddu", 3e-2))):
+            J = J + pb.QuadraticRegularizer(name, traj, R, dt_power=pw)
+            rows = traj.components[name]
+            jr, gv, gdt = OB.quadratic_regularizer(Z[rows.start:rows.stop], Z[p.n_x], R, dt_power=pw)
+            Jo += jr
+            G[rows.start:rows.stop] += gv
+            G[p.n_x] += gdt
+        val, _ = _obj_check(J, Z, Jo, G.reshape(-1, order="F"))
+        J.close()
+    # the reference's converged solution: the infidelity part vanishes
+    traj = pb.NamedTrajectory.smooth_pulse_layout(Zg, p.n_x, p.m, "Ũ⃗")
+    J = pb.UnitaryInfidelityObjective(CX, "Ũ⃗", traj)
+    assert 0 <= pb.objective_value(J, traj) < 1e-5
+    J.close()
+    # MultiKetTrajectory solution: coherent and per-state ket losses
+    probs, Zm = GU.load_multi()
+    traj = pb.NamedTrajectory.multi_state_layout(Zm, ["ψ̃1", "ψ̃2"], 4, 2)
+    p0, p1 = np.array([1, 0], complex), np.array([0, 1], complex)
+    for w in (None, [0.9, 0.1], [0.5, 0.5]):
+        J = pb.CoherentKetInfidelityObjective([p1, p0], ["ψ̃1", "ψ̃2"], traj, Q=100.0, weights=w)
+        Jo, gs = OB.coherent_ket_infidelity([Zm[0:4, -1], Zm[4:8, -1]], [p1, p0], 100.0, w)
+        G = np.zeros_like(Zm)
+        G[0:4, -1], G[4:8, -1] = gs
+        _obj_check(J, Zm, Jo, G.reshape(-1, order="F"))
+        J.close()
+    J = pb.KetInfidelityObjective(p1, "ψ̃1", traj) + pb.KetInfidelityObjective(p0, "ψ̃2", traj)
+    (j1, g1), (j2, g2) = OB.ket_infidelity(Zm[0:4, -1], p1), OB.ket_infidelity(Zm[4:8, -1], p0)
+    G = np.zeros_like(Zm)
+    G[0:4, -1], G[4:8, -1] = g1, g2
+    val, _ = _obj_check(J, Zm, j1 + j2, G.reshape(-1, order="F"))
+    assert val < 1e-3
+    J.close()
+
+
+def test_objective_kats_through_the_c_abi():
+    """The values the reference's own tests expect (objectives.jl:537, 559, 592-593), on the device."""
+    N = 10
+    p0, p1 = np.array([1, 0], complex), np.array([0, 1], complex)
+    iso = lambda v: np.concatenate([v.real, v.imag])
+    rng = np.random.default_rng(2)
+
+    def traj_of(a, b):
+        Z = np.zeros((10, N))
+        Z[0:4], Z[4:8] = iso(a)[:, None], iso(b)[:, None]
+        Z[8], Z[9] = 0.1, 0.0
+        Z[9] = rng.standard_normal(N)
+        return pb.NamedTrajectory(Z, {"ψ̃1": range(0, 4), "ψ̃2": range(4, 8), "Δt": range(8, 9), "u": range(9, 10)})
+
+    goals, names = [p1, p0], ["ψ̃1", "ψ̃2"]
+    t = traj_of(p1, 0.5 * p0)
+    J1 = pb.CoherentKetInfidelityObjective(goals, names, t, Q=100.0, weights=[0.9, 0.1])
+    J2 = pb.CoherentKetInfidelityObjective(goals, names, t, Q=100.0, weights=[0.1, 0.9])
+    assert np.isclose(pb.objective_value(J1, t), 100.0 * (1 - 0.9025), rtol=1e-12)
+    assert np.isclose(pb.objective_value(J2, t), 100.0 * (1 - 0.3025), rtol=1e-12)
+    Ju = pb.CoherentKetInfidelityObjective(goals, names, t, Q=100.0)
+    Jw = pb.CoherentKetInfidelityObjective(goals, names, t, Q=100.0, weights=[0.5, 0.5])
+    assert pb.objective_value(Ju, t) == pb.objective_value(Jw, t)          # uniform weights: bit-for-bit
+    g = np.zeros(t.dim * t.N + t.global_dim)
+    pb.gradient_(g, J1, t)
+    assert not np.all(g == 0)
+    assert pb.objective_value(Ju, traj_of(p1, p0)) < 1e-10                 # perfect coherent transfer
+    assert pb.objective_value(Ju, traj_of(p1, -p0)) > 50.0                 # opposite phases: F = 0
+
+
+def test_objective_kinds_edge_cases_and_full_size():
+    from oracle import objectives as OB
+    from oracle import isomorphisms as ISO
+    rng = np.random.default_rng(31)
+    cplx = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    # density matrix (compact iso, linear loss) + leakage at a subset of knots + regularizer with baseline / times
+    n, K, m = 3, 37, 2
+    D = n * n + 2 + 3 * m
+    Z = np.asfortranarray(0.4 * rng.standard_normal((D, K)))
+    Z[n * n] = 0.05 + 0.1 * rng.random(K)
+    traj = pb.NamedTrajectory.smooth_pulse_layout(Z, n * n, m, "ρ⃗̃")
+    A = cplx(n, n)
+    rho_g = A @ A.conj().T
+    rho_g /= np.trace(rho_g).real
+    psi = cplx(n)
+    psi /= np.linalg.norm(psi)
+    times, Qs, idx = np.array([0, 5, 6, K - 1]), np.array([1.0, 0.5, 2.0, 3.0]), [2, 5, 7]
+    base = rng.standard_normal((m, K))
+    J = (pb.DensityMatrixInfidelityObjective("ρ⃗̃", rho_g, traj, Q=50.0)
+         + pb.DensityMatrixPureStateInfidelityObjective("ρ⃗̃", psi, traj, Q=7.0)
+         + pb.LeakageObjective(idx, "ρ⃗̃", traj, times=times, Qs=Qs)
+         + pb.QuadraticRegularizer("u", traj, [0.3, 0.7], baseline=base, times=np.arange(1, K - 1), dt_power=1)
+         + pb.QuadraticRegularizer("u", traj, 0.1))                       # two regularizers on the same rows
+    G = np.zeros_like(Z)
+    j1, g1 = OB.density_infidelity(Z[:n * n, -1], rho_g, 50.0)
+    j2, g2 = OB.density_pure_state_infidelity(Z[:n * n, -1], psi, 7.0)
+    G[:n * n, -1] = g1 + g2
+    j3, g3 = OB.leakage(Z[:n * n][:, times], idx, Qs)
+    G[:n * n, times] += g3
+    u = traj.components["u"]
+    tt = np.arange(1, K - 1)
+    j4, gv, gdt = OB.quadratic_regularizer(Z[u.start:u.stop][:, tt], Z[n * n, tt], [0.3, 0.7], base[:, tt], 1)
+    G[u.start:u.stop, 1:K - 1] += gv
+    G[n * n, 1:K - 1] += gdt
+    j5, gv5, _ = OB.quadratic_regularizer(Z[u.start:u.stop], Z[n * n], 0.1)
+    G[u.start:u.stop] += gv5
+    _obj_check(J, Z, j1 + j2 + j3 + j4 + j5, G.reshape(-1, order="F"))
+    J.close()
+    # EmbeddedOperator subspace fidelity (objectives.jl:339-345): 3-level transmon, qubit subspace
+    N, sub = 3, [0, 1]
+    Zu = np.asfortranarray(0.5 * rng.standard_normal((2 * N * N + 2 + 3, 5)))
+    traj = pb.NamedTrajectory.smooth_pulse_layout(Zu, 2 * N * N, 1, "Ũ⃗")
+    Us = np.linalg.qr(cplx(2, 2))[0]
+    J = pb.UnitaryInfidelityObjective(Us, "Ũ⃗", traj, Q=100.0, subspace=sub)
+    jo, go = OB.unitary_infidelity(Zu[:2 * N * N, -1], Us, 100.0, subspace=sub)
+    G = np.zeros_like(Zu)
+    G[:2 * N * N, -1] = go
+    _obj_check(J, Zu, jo, G.reshape(-1, order="F"))
+    J.close()
+    with pytest.raises(ValueError):
+        pb.UnitaryInfidelityObjective(2 * Us, "Ũ⃗", traj, subspace=sub)      # subspace form needs a unitary goal
+    # K = 1 (terminal knot is the only knot) and an empty objective
+    t1 = pb.NamedTrajectory.smooth_pulse_layout(Zu[:, :1].copy(), 2 * N * N, 1, "Ũ⃗")
+    J = pb.UnitaryInfidelityObjective(np.eye(N), "Ũ⃗", t1)
+    jo, go = OB.unitary_infidelity(Zu[:2 * N * N, 0], np.eye(N), 100.0)
+    _obj_check(J, Zu[:, :1], jo, np.concatenate([go, np.zeros(5)]))
+    J.close()
+    E = pb.B200Objective(traj)
+    val, g = E.value_gradient(Zu)
+    assert val == 0.0 and not g.any()
+    E.close()
+    # bad rows / times are rejected by the library
+    with pytest.raises(pb.PB2Error):
+        pb.LeakageObjective([0], "Ũ⃗", traj, times=[99]).value(Zu)
+    # full BASELINE C3 size: identity propagator at every knot => J = 0, perturbed => oracle
+    p, Z, _ = C.trajectory(3)
+    traj = pb.NamedTrajectory(Z, {"Ũ⃗": range(p.x_off, p.x_off + p.n_x), "Δt": range(p.dt_off, p.dt_off + 1),
+                                  "u": range(p.u_off, p.u_off + p.m)})
+    Ug = np.linalg.qr(cplx(8, 8))[0]
+    J = pb.UnitaryInfidelityObjective(Ug, "Ũ⃗", traj) + pb.QuadraticRegularizer("u", traj, 1e-2, dt_power=2)
+    jo, go = OB.unitary_infidelity(Z[p.x_off:p.x_off + p.n_x, -1], Ug, 100.0)
+    jr, gv, gdt = OB.quadratic_regularizer(Z[p.u_off:p.u_off + p.m], Z[p.dt_off], 1e-2, dt_power=2)
+    G = np.zeros_like(Z)
+    G[p.x_off:p.x_off + p.n_x, -1] = go
+    G[p.u_off:p.u_off + p.m] += gv
+    G[p.dt_off] += gdt
+    _obj_check(J, Z, jo + jr, G.reshape(-1, order="F"))
+    Zp = Z.copy(order="F")
+    Zp[p.x_off:p.x_off + p.n_x, -1] = ISO.operator_to_iso_vec(np.exp(0.3j) * Ug)
+    Jt = pb.UnitaryInfidelityObjective(Ug, "Ũ⃗", traj)
+    assert Jt.value(Zp) < 1e-10
+    # device-pointer entry point on the caller's stream
+    import torch
+    dZ = torch.from_numpy(np.ascontiguousarray(Z.T)).cuda()       # knot-major = rows of Z.T
+    dJ, dg = torch.zeros(1, dtype=torch.float64, device="cuda"), torch.empty(Z.size, dtype=torch.float64, device="cuda")
+    J.value_gradient_device(dZ, dJ, dg, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    val, g = J.value_gradient(Z)
+    assert dJ.item() == val and np.array_equal(dg.cpu().numpy(), g)
+    J.close()
+    Jt.close()

@@ -192,3 +192,91 @@ def test_multi_ket_golden_is_a_valid_input():
         d = KN.residual(p, Z)
         assert np.abs(d).max() < 1e-2                      # smooth_pulse_problem.jl:781-784
         assert np.abs(d - CP.residual(p, Z)).max() < 1e-12  # both oracle algorithms agree on it
+
+
+# ---- objectives ---------------------------------------------------------------
+def _fd(f, x, h=1e-6):
+    g = np.zeros_like(x)
+    for i in range(x.size):
+        e = np.zeros_like(x)
+        e[i] = h
+        g[i] = (f(x + e) - f(x - e)) / (2 * h)
+    return g
+
+
+def test_objective_kats_from_the_reference_tests():
+    """The numeric expectations the reference's own objective tests hold (objectives.jl:483-667)."""
+    from oracle import objectives as OB
+    p0, p1 = np.array([1, 0], complex), np.array([0, 1], complex)
+    goals = [p1, p0]
+    asym = [iso.ket_to_iso(p1), iso.ket_to_iso(0.5 * p0)]
+    # :592-593  F = |0.9*1 + 0.1*1/2|^2 = 0.9025 and |0.1*1 + 0.9*1/2|^2 = 0.3025
+    assert np.isclose(OB.coherent_ket_infidelity(asym, goals, 100.0, [0.9, 0.1])[0], 100.0 * (1 - 0.9025), rtol=1e-12)
+    assert np.isclose(OB.coherent_ket_infidelity(asym, goals, 100.0, [0.1, 0.9])[0], 100.0 * (1 - 0.3025), rtol=1e-12)
+    # :648-657 weighted mean normalised by the weight sum; only ratios matter
+    assert np.isclose(OB.coherent_ket_fidelity(asym, goals, [0.9, 0.1]), abs(0.9 * 1 + 0.1 * 0.5) ** 2)
+    assert np.isclose(OB.coherent_ket_fidelity(asym, goals, [9.0, 1.0]), OB.coherent_ket_fidelity(asym, goals, [0.9, 0.1]))
+    # :660-666 uniform weights are bit-for-bit the unweighted value, also when 1/n is inexact
+    x3, g3 = [iso.ket_to_iso(p1), iso.ket_to_iso(0.5 * p0), iso.ket_to_iso(0.25 * p1)], [p1, p0, p1]
+    F = OB.coherent_ket_fidelity(x3, g3)
+    assert OB.coherent_ket_fidelity(x3, g3, [1 / 3] * 3) == F and OB.coherent_ket_fidelity(x3, g3, [1.0] * 3) == F
+    # :537 perfect coherent transfer, :559 opposite phases give F = 0
+    assert OB.coherent_ket_infidelity([iso.ket_to_iso(p1), iso.ket_to_iso(p0)], goals)[0] < 1e-10
+    assert OB.coherent_ket_infidelity([iso.ket_to_iso(p1), iso.ket_to_iso(-p0)], goals)[0] > 50.0
+    # :627 identical kets
+    assert np.isclose(OB.coherent_ket_fidelity([iso.ket_to_iso(p1), iso.ket_to_iso(p0)], goals), 1.0)
+
+
+def test_objectives_on_the_reference_solutions():
+    """The reference's converged two-qubit solution was obtained by minimising exactly this objective
+    (smooth_pulse_problem.jl:534-542): its terminal unitary is CX up to a global phase, so the
+    restated loss must vanish there; same for the coherent ket loss on the MultiKetTrajectory solution."""
+    from oracle import objectives as OB
+    p, Z = GU.load("two_qubit_zoh")
+    CX = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], complex)
+    J, g = OB.unitary_infidelity(Z[:p.n_x, -1], CX, 100.0)
+    assert 0 <= J < 1e-5
+    probs, Zm = GU.load_multi()
+    p0, p1 = np.array([1, 0], complex), np.array([0, 1], complex)
+    Jc, _ = OB.coherent_ket_infidelity([Zm[0:4, -1], Zm[4:8, -1]], [p1, p0], 100.0)
+    assert 0 <= Jc < 1e-3
+    for x, goal in ((Zm[0:4, -1], p1), (Zm[4:8, -1], p0)):
+        assert OB.ket_infidelity(x, goal, 100.0)[0] < 1e-3
+
+
+def test_objective_gradients_vs_finite_differences():
+    from oracle import objectives as OB
+    rng = np.random.default_rng(11)
+    cplx = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    g = cplx(4)
+    g /= np.linalg.norm(g)
+    for x in (rng.standard_normal(8), 0.3 * rng.standard_normal(8)):      # F > 1 and F < 1 branches of |1 - F|
+        assert np.abs(OB.ket_infidelity(x, g)[1] - _fd(lambda y: OB.ket_infidelity(y, g)[0], x)).max() < 1e-6
+    n = 4
+    x = 0.3 * rng.standard_normal(2 * n * n)
+    Ug = np.linalg.qr(cplx(n, n))[0]
+    assert np.abs(OB.unitary_infidelity(x, Ug)[1] - _fd(lambda y: OB.unitary_infidelity(y, Ug)[0], x)).max() < 1e-6
+    sub, Us = [0, 2], np.linalg.qr(cplx(2, 2))[0]
+    f = lambda y: OB.unitary_infidelity(y, Us, subspace=sub)[0]
+    assert np.abs(OB.unitary_infidelity(x, Us, subspace=sub)[1] - _fd(f, x)).max() < 1e-6
+    x = 0.3 * rng.standard_normal(9)
+    A = cplx(3, 3)
+    rg = A @ A.conj().T
+    rg /= np.trace(rg).real
+    assert np.abs(OB.density_infidelity(x, rg)[1] - _fd(lambda y: OB.density_infidelity(y, rg)[0], x)).max() < 1e-6
+    psi = cplx(3)
+    psi /= np.linalg.norm(psi)
+    f = lambda y: OB.density_pure_state_infidelity(y, psi)[0]
+    assert np.abs(OB.density_pure_state_infidelity(x, psi)[1] - _fd(f, x)).max() < 1e-6
+    # density loss agrees with the definition on a physical state: tr(rho rho) of a pure state is 1
+    rho = np.outer(psi, psi.conj())
+    assert OB.density_infidelity(iso.density_to_compact_iso(rho), rho)[0] < 1e-12
+    assert OB.density_pure_state_infidelity(iso.density_to_compact_iso(rho), psi)[0] < 1e-12
+    # identical unitary up to a global phase
+    assert OB.unitary_infidelity(iso.operator_to_iso_vec(np.exp(0.7j) * Ug), Ug)[0] < 1e-10
+    V, dt = rng.standard_normal((3, 7)), 0.1 + rng.random(7)
+    for pw in (0, 1, 2):
+        J, gV, gdt = OB.quadratic_regularizer(V, dt, [1.0, 2.0, 0.5], dt_power=pw)
+        f = lambda y: OB.quadratic_regularizer(y[:21].reshape(3, 7), y[21:], [1.0, 2.0, 0.5], dt_power=pw)[0]
+        fd = _fd(f, np.concatenate([V.reshape(-1), dt]))
+        assert np.abs(np.concatenate([gV.reshape(-1), gdt]) - fd).max() < 1e-6
