@@ -64,7 +64,9 @@ enum {
 typedef struct pb2_desc {
   int32_t kind;        /* PB2_KET | PB2_UNITARY | PB2_DENSITY */
   int32_t b;           /* generator block size: 2d (ket, unitary) or d^2 (density) */
-  int32_t n_b;         /* state columns sharing the generator: d for unitary, 1 otherwise */
+  int32_t n_b;         /* contiguous state blocks sharing the generator: d for unitary; 1 for one ket /
+                          density, or the number of states of a MultiKetTrajectory / MultiDensityTrajectory
+                          (one system, src/control/integrators.jl:102-117) fused into one integrator */
   int32_t m;           /* number of (linear) drives */
   int32_t K;           /* knot columns in the Z passed to this handle -> K-1 constraints */
   int32_t D;           /* reals per knot (traj.dim) */

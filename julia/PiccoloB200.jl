@@ -173,6 +173,104 @@ function DirectTrajOpt.jacobian!(vals::AbstractVector{Float64}, B::B200Derivativ
     return nothing
 end
 
+# ---- objective value + gradient (pb2_obj_*) -----------------------------------------------------------
+# One device handle for a whole sum of objectives.  A term is the real form of one of
+# src/control/objectives.jl's losses (see include/piccolo_b200.h); the constructors below rewrite the
+# complex goal as coefficient vectors exactly as piccolo.jl_b200/objectives.py does.
+struct PB2ObjTerm
+    flags::Int32
+    n_rows::Int32
+    rows::Ptr{Int32}
+    a_re::Ptr{Float64}
+    a_im::Ptr{Float64}
+    a_sq::Ptr{Float64}
+    a_lin::Ptr{Float64}
+    scale::Float64
+    n_times::Int32
+    times::Ptr{Int32}
+    Q::Ptr{Float64}
+end
+
+struct PB2ObjReg
+    n_rows::Int32
+    rows::Ptr{Int32}
+    R::Ptr{Float64}
+    baseline::Ptr{Float64}
+    dt_power::Int32
+    n_times::Int32
+    times::Ptr{Int32}
+end
+
+struct PB2ObjDesc
+    K::Int32
+    D::Int32
+    dt_off::Int32
+    n_terms::Int32
+    n_regs::Int32
+    terms::Ptr{PB2ObjTerm}
+    regs::Ptr{PB2ObjReg}
+    device::Int32
+end
+
+mutable struct B200Objective <: DirectTrajOpt.Objectives.AbstractObjective
+    handle::Ptr{Cvoid}
+    n::Int                      # traj.dim * traj.N
+end
+
+# ⟨goal|ψ⟩ for ψ̃ = [Re ψ; Im ψ]
+overlap_coeffs(g::AbstractVector{<:Complex}) = (vcat(real(g), imag(g)), vcat(-imag(g), real(g)))
+
+"""
+    B200UnitaryInfidelityObjective(U_goal, name, traj; Q, R = (u = 1e-2, ...), dt_power = 0)
+
+`UnitaryInfidelityObjective(U_goal, name, traj; Q) + Σ QuadraticRegularizer(sym, traj, R[sym])`
+(smooth_pulse_problem.jl:240-250) as one device handle.
+"""
+function B200UnitaryInfidelityObjective(U_goal::AbstractMatrix{<:Complex}, name::Symbol, traj::NamedTrajectory;
+                                        Q = 100.0, R = NamedTuple(), dt_power = 0, device = 0)
+    n = size(U_goal, 1)
+    rows = Int32.(collect(traj.components[name]) .- 1)
+    a_re = zeros(length(rows)); a_im = zeros(length(rows))
+    for c = 1:n
+        r, i = overlap_coeffs(U_goal[:, c])
+        a_re[(2n*(c-1)+1):(2n*c)] = r
+        a_im[(2n*(c-1)+1):(2n*c)] = i
+    end
+    Qv = [Float64(Q)]
+    reg_rows = [Int32.(collect(traj.components[s]) .- 1) for s in keys(R)]
+    reg_R = [fill(Float64(R[s]), length(traj.components[s])) for s in keys(R)]
+    GC.@preserve rows a_re a_im Qv reg_rows reg_R begin
+        terms = [PB2ObjTerm(1, length(rows), pointer(rows), pointer(a_re), pointer(a_im), C_NULL, C_NULL,
+                            1 / n^2, 0, C_NULL, pointer(Qv))]
+        regs = [PB2ObjReg(length(reg_rows[i]), pointer(reg_rows[i]), pointer(reg_R[i]), C_NULL, dt_power, 0, C_NULL)
+                for i in eachindex(reg_rows)]
+        GC.@preserve terms regs begin
+            desc = PB2ObjDesc(traj.N, traj.dim, first(traj.components[traj.timestep]) - 1, 1, length(regs),
+                              pointer(terms), isempty(regs) ? C_NULL : pointer(regs), device)
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:pb2_obj_create, LIB), Cint, (Ref{PB2ObjDesc}, Ref{Ptr{Cvoid}}), desc, h))
+        end
+    end
+    J = B200Objective(h[], traj.dim * traj.N)
+    finalizer(J -> ccall((:pb2_obj_destroy, LIB), Cvoid, (Ptr{Cvoid},), J.handle), J)
+    return J
+end
+
+function DirectTrajOpt.objective_value(J::B200Objective, traj::NamedTrajectory)
+    v = Ref{Float64}(0.0)
+    check(ccall((:pb2_obj_value_gradient, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Cint),
+                J.handle, traj.datavec, v, C_NULL, PB2_HOST))
+    return v[]
+end
+
+function DirectTrajOpt.gradient!(∇::AbstractVector{Float64}, J::B200Objective, traj::NamedTrajectory)
+    v = Ref{Float64}(0.0)
+    fill!(view(∇, (J.n+1):length(∇)), 0.0)          # global variables: no dependence
+    check(ccall((:pb2_obj_value_gradient, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Cint),
+                J.handle, traj.datavec, v, ∇, PB2_HOST))
+    return nothing
+end
+
 # ---- registry hook: `integrator = "b200_bilinear"` in a ProblemSpec ---------------------------------
 # factory signature (qtraj, N; alg) -> integrator            src/specs/materialize.jl:216-222
 function __init__()

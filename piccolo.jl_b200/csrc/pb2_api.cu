@@ -330,8 +330,6 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     return fail(PB2_EINVAL, "pb2_create: ket/unitary generators have even size 2d");
   if (d.kind == PB2_UNITARY && d.n_b * 2 != d.b)
     return fail(PB2_EINVAL, "pb2_create: unitary needs n_b = b/2");
-  if (d.kind != PB2_UNITARY && d.n_b != 1)
-    return fail(PB2_EINVAL, "pb2_create: ket/density need n_b = 1");
   const int n_x = d.b * d.n_b;
   auto inside = [&](int off, int len) { return off >= 0 && off + len <= d.D; };
   if (!inside(d.x_off, n_x) || !inside(d.dt_off, 1) || !inside(d.u_off, d.m))

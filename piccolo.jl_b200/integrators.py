@@ -155,7 +155,7 @@ class B200BilinearIntegrator:
     """
 
     def __init__(self, kind, G_drift, G_drives, *, K, D, x_off, dt_off, u_off, x_name="x",
-                 u_name="u", device=0, algorithm="auto", knot0=0, global_dim=0):
+                 u_name="u", device=0, algorithm="auto", knot0=0, global_dim=0, n_states=1):
         self._lib = capi.load_library()
         G0 = np.asfortranarray(G_drift, dtype=np.float64)
         b = G0.shape[0]
@@ -163,7 +163,9 @@ class B200BilinearIntegrator:
         Gj = (np.concatenate([np.asfortranarray(g, dtype=np.float64).reshape(-1, order="F")
                               for g in G_drives]) if m else np.zeros(1))
         self.kind, self.b, self.m = kind, b, m
-        self.n_b = b // 2 if kind == "unitary" else 1
+        if kind == "unitary" and n_states != 1:
+            raise ValueError("n_states applies to ket / density blocks sharing one generator")
+        self.n_b = b // 2 if kind == "unitary" else int(n_states)
         self.x_dim = b * self.n_b
         self.K, self.D = int(K), int(D)
         self.x_off, self.dt_off, self.u_off = int(x_off), int(dt_off), int(u_off)
@@ -359,6 +361,21 @@ def BilinearIntegrator(qtraj, traj_or_N, traj=None, **kw):
     the reference rebuilds it from ``qtraj`` and ``N``, here it is passed in."""
     if isinstance(traj_or_N, NamedTrajectory):
         traj = traj_or_N
+    if kw.pop("fused", False):
+        # every state of a MultiKetTrajectory obeys the same generator and the blocks are contiguous in
+        # the knot column, so one integrator (one launch) can evaluate them all: rows are knot-major,
+        # state-major inside a knot (the per-state vector below is state-major, knot-major inside)
+        if not isinstance(qtraj, MultiKetTrajectory) or traj is None:
+            raise TypeError("fused=True needs a MultiKetTrajectory and its NamedTrajectory")
+        comps = traj.components
+        blocks = [comps[n] for n in qtraj.state_names]
+        if any(b.start != a.stop for a, b in zip(blocks, blocks[1:])) or len({len(b) for b in blocks}) != 1:
+            raise ValueError("state blocks must be contiguous and equally sized")
+        G0, Gj = qtraj.system.G_parts()
+        return B200BilinearIntegrator(
+            qtraj.kind, G0, Gj, K=traj.N, D=traj.dim, x_off=blocks[0].start, dt_off=comps[traj.timestep].start,
+            u_off=comps["u"].start, x_name="+".join(qtraj.state_names), global_dim=traj.global_dim,
+            n_states=len(blocks), **kw)
     if isinstance(qtraj, (MultiKetTrajectory, SamplingTrajectory)) and traj is not None:
         # a vector of integrators, one per state block, all reading the same Δt / u rows
         systems = qtraj.systems if isinstance(qtraj, SamplingTrajectory) else [qtraj.system] * len(qtraj.state_names)

@@ -733,3 +733,83 @@ def test_objective_kinds_edge_cases_and_full_size():
     assert dJ.item() == val and np.array_equal(dg.cpu().numpy(), g)
     J.close()
     Jt.close()
+
+
+# ---- fused multi-state integrator: all kets of a MultiKetTrajectory in one launch --------------------
+def test_fused_multi_ket_integrator_matches_per_state_integrators():
+    """n_b = number of states sharing the generator.  Same numbers as the vector of per-state integrators
+    (integrators.jl:102-117), rows knot-major instead of state-major; checked on the reference's own
+    MultiKetTrajectory solution, against the oracle, for the general kernels and the 8-ket 3-qubit shape
+    (which runs the headline kernel)."""
+    import dataclasses
+    probs, Z = GU.load_multi()
+    sys_ = pb.QuantumSystem(np.diag([1.0, -1.0]), [np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]])], [1, 1])
+    qtraj = pb.MultiKetTrajectory(sys_, len(probs))
+    traj = pb.NamedTrajectory.multi_state_layout(Z, qtraj.state_names, probs[0].b, probs[0].m)
+    n_s, b, K = len(probs), probs[0].b, probs[0].K
+    pf = dataclasses.replace(probs[0], n_b=n_s, x_off=0)
+    mu = np.random.default_rng(4).standard_normal(pf.dim)
+    for alg in ("generic", "auto"):
+        F = pb.BilinearIntegrator(qtraj, traj, fused=True, algorithm=alg)
+        assert F.dim == n_s * b * (K - 1) and F.n_b == n_s
+        check_all(pf, Z, mu, F)
+        r, c = F.jacobian_structure()
+        ro, co = KN.jacobian_structure(pf)
+        assert np.array_equal(r, ro) and np.array_equal(c, co)
+        hr, hc = F.hessian_structure()
+        hro, hco = KN.hessian_structure(pf)
+        assert np.array_equal(hr, hro) and np.array_equal(hc, hco)
+        d, v = F.residual_jacobian(Z)
+        Bs = pb.BilinearIntegrator(qtraj, traj, algorithm=alg)
+        for s, B in enumerate(Bs):
+            ds, vs = B.residual_jacobian(Z)
+            # residual rows of state s inside the fused knot-major vector
+            assert np.abs(d.reshape(K - 1, n_s, b)[:, s].reshape(-1) - ds).max() < 1e-14
+            # same sparse matrix: compare as dense blocks through the COO structure
+            rs, cs = B.jacobian_structure()
+            fused = {(int(a) , int(bb)): x for a, bb, x in zip(r, c, v)}
+            k_of, i_of = (rs - 1) // b, (rs - 1) % b
+            rows_f = k_of * (n_s * b) + s * b + i_of + 1
+            got = np.array([fused[(int(a), int(bb))] for a, bb in zip(rows_f, cs)])
+            assert np.abs(got - vs).max() < 1e-13
+            B.close()
+        F.close()
+    with pytest.raises(TypeError):
+        pb.BilinearIntegrator(pb.KetTrajectory(sys_), traj, fused=True)
+    # random 3-state, 2-level problem and a fused density pair (generic kernel)
+    rng = np.random.default_rng(14)
+    for kind, bsz, n_s in (("ket", 4, 3), ("ket", 6, 5), ("density", 4, 2)):
+        m, K = 2, 19
+        if kind == "ket":
+            H0 = rng.standard_normal((bsz // 2, bsz // 2)); H0 = H0 + H0.T
+            Hd = [rng.standard_normal((bsz // 2, bsz // 2)) + 1j * rng.standard_normal((bsz // 2, bsz // 2)) for _ in range(m)]
+            s_ = pb.QuantumSystem(H0, [h + h.conj().T for h in Hd], [1] * m)
+            G0, Gj = s_.G_parts()
+        else:
+            G0, Gj = rng.standard_normal((bsz, bsz)), [rng.standard_normal((bsz, bsz)) for _ in range(m)]
+        base = KN.make_problem(kind, G0, Gj, K)
+        D = n_s * bsz + 2 + 3 * m
+        pf = dataclasses.replace(base, n_b=n_s, D=D, x_off=0, dt_off=n_s * bsz, u_off=n_s * bsz + 2)
+        Zr = np.asfortranarray(0.4 * rng.standard_normal((D, K)))
+        Zr[pf.dt_off] = 0.05 + 0.1 * rng.random(K)
+        for alg in algorithms(pf):
+            F = pb.B200BilinearIntegrator(kind, G0, list(Gj), K=K, D=D, x_off=0, dt_off=pf.dt_off, u_off=pf.u_off,
+                                          n_states=n_s, algorithm=alg)
+            check_all(pf, Zr, rng.standard_normal(pf.dim), F)
+            F.close()
+    # eight kets of the 3-qubit system: the fused integrator has the unitary's shape and runs knot_u8 / knot_u8h
+    p3, Z3, mu3 = C.trajectory(3, 45)
+    F = pb.B200BilinearIntegrator("ket", p3.G0, list(p3.Gj), K=p3.K, D=p3.D, x_off=p3.x_off, dt_off=p3.dt_off,
+                                  u_off=p3.u_off, n_states=8)
+    U = make(p3)
+    assert F.algorithm == "dmma" and F.compact_stride == U.compact_stride > 0
+    d, v = F.residual_jacobian(Z3)
+    du, vu = U.residual_jacobian(Z3)
+    assert np.array_equal(d, du) and np.array_equal(v, vu)
+    assert np.array_equal(F.hessian_values(Z3, mu3), U.hessian_values(Z3, mu3))
+    check_all(p3, Z3, mu3, F)
+    F.close()
+    U.close()
+    with pytest.raises(ValueError):
+        pb.B200BilinearIntegrator("unitary", p3.G0, list(p3.Gj), K=p3.K, D=p3.D, x_off=0, dt_off=p3.dt_off,
+                                  u_off=p3.u_off, n_states=2)
