@@ -46,6 +46,7 @@ struct ObjParams {
 };
 
 constexpr int kObjThreads = 128;
+constexpr int kObjRegs = 8;       // regularizers whose metadata is staged in shared memory
 
 // block-wide sums of N values; every thread returns with the totals (fixed order => deterministic)
 template <int N>
@@ -74,8 +75,22 @@ __global__ void __launch_bounds__(kObjThreads) knot_objective_kernel(ObjParams p
   double* g = smem_obj + p.D;
   __shared__ double red[4 * (kObjThreads / 32)];
   __shared__ bool last;
+  // per-knot metadata of the regularizers, fetched in parallel with the knot column (one round trip
+  // instead of a chain of dependent loads per regularizer)
+  __shared__ int r_o0[kObjRegs], r_n[kObjRegs], r_pw[kObjRegs];
+  __shared__ double r_act[kObjRegs];
+  __shared__ const double* r_b[kObjRegs];
+  __shared__ int it_range[2];
   const int k = blockIdx.x, tid = threadIdx.x;
   const double* Zk = p.Z + (size_t)k * p.D;
+  if (tid < p.n_regs && tid < kObjRegs) {
+    r_o0[tid] = p.r_off[tid];
+    r_n[tid] = p.r_off[tid + 1] - p.r_off[tid];
+    r_pw[tid] = p.r_pow[tid];
+    r_act[tid] = p.r_w[(size_t)tid * p.K + k];
+    r_b[tid] = p.r_base[tid];
+  }
+  if (tid >= kObjThreads - 2) it_range[tid - (kObjThreads - 2)] = p.knot_ptr[k + tid - (kObjThreads - 2)];
   for (int i = tid; i < p.D; i += kObjThreads) {
     z[i] = Zk[i];
     g[i] = 0.0;
@@ -83,7 +98,7 @@ __global__ void __launch_bounds__(kObjThreads) knot_objective_kernel(ObjParams p
   __syncthreads();
   double Jk = 0.0;
 
-  for (int it = p.knot_ptr[k]; it < p.knot_ptr[k + 1]; ++it) {
+  for (int it = it_range[0]; it < it_range[1]; ++it) {
     const int t = p.item_term[it];
     const double Q = p.item_q[it];
     const int o0 = p.t_off[t], n = p.t_off[t + 1] - o0;
@@ -117,11 +132,13 @@ __global__ void __launch_bounds__(kObjThreads) knot_objective_kernel(ObjParams p
 
   const double dt = z[p.dt_off];
   for (int r = 0; r < p.n_regs; ++r) {
-    if (p.r_w[(size_t)r * p.K + k] == 0.0) continue;
-    const int o0 = p.r_off[r], n = p.r_off[r + 1] - o0, pw = p.r_pow[r];
+    const bool cached = r < kObjRegs;
+    if ((cached ? r_act[r] : p.r_w[(size_t)r * p.K + k]) == 0.0) continue;
+    const int o0 = cached ? r_o0[r] : p.r_off[r], n = cached ? r_n[r] : p.r_off[r + 1] - o0;
+    const int pw = cached ? r_pw[r] : p.r_pow[r];
     const double dtp = pw == 0 ? 1.0 : (pw == 1 ? dt : dt * dt);
     const double ddtp = pw == 0 ? 0.0 : (pw == 1 ? 1.0 : 2.0 * dt);
-    const double* base = p.r_base[r];
+    const double* base = cached ? r_b[r] : p.r_base[r];
     double q[1] = {0.0};
     for (int i = tid; i < n; i += kObjThreads) {
       const int row = p.r_rows[o0 + i];

@@ -1,3 +1,4 @@
+"""Smallest exercise of the warp-specialised kernels for `compute-sanitizer --tool racecheck`."""
 import sys, numpy as np
 sys.path.insert(0, "/root/repo")
 import piccolo_b200 as pb

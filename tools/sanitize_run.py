@@ -33,3 +33,10 @@ for cfg, K in ((3, 700), (2, 60), (4, 50), (1, 20)):
     L.residual_jacobian(Z)
     L.hessian_values(np.ones(L.dim))
     L.close()
+    if p.kind == "unitary":
+        n = int(round((p.n_x // 2) ** 0.5))
+        J = (pb.UnitaryInfidelityObjective(np.eye(n), "x", traj) + pb.QuadraticRegularizer("u", traj, 1e-2, dt_power=1)
+             + pb.LeakageObjective([0, 1], "x", traj, times=[0, K // 2, K - 1]))
+        J.value_gradient(Z)
+        J.value(Z)
+        J.close()
