@@ -77,6 +77,14 @@ __device__ __forceinline__ void stg_f64x2(double* ptr, double a, double b) {
   asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(ptr), "d"(a), "d"(b) : "memory");
 }
 
+// the per-step exchange barrier; the debug build can drop it (PB2_DRY=3: wrong numbers, upper bound
+// on what decoupling the warps of a group could gain)
+#ifdef PB2_TRACE
+#define U8_BAR(id, n) do { if ((id) >= 0) bar_sync((id), (n)); } while (0)
+#else
+#define U8_BAR(id, n) bar_sync((id), (n))
+#endif
+
 // byte offset of element i (row 8 (i>>1) + 2q + (i&1)) relative to the lane's (column, 2q) address
 #define U8_OFF(i) (((i) >> 1) * 64 + ((i) & 1) * 8)
 
@@ -144,7 +152,7 @@ __device__ __forceinline__ void u8_step_ex(double (&tE)[4], double (&tX)[4], con
   double dE[2][2], dX[2][2];
   u8_mma(dX, tX, A);
   u8_mma(dE, tE, A);
-  bar_sync(xbar, nx);
+  U8_BAR(xbar, nx);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     tX[i] = fma(ck, bX[i], dX[i >> 1][i & 1]);
@@ -168,7 +176,7 @@ __device__ __forceinline__ void u8_step_jets(double (&t)[2][4], const double (&b
   }
   double ck = 0.0;
   if (!FIRST) ck = lds_f64<0>(ck_addr);
-  bar_sync(xbar, nx);
+  U8_BAR(xbar, nx);
   double y[2][4][W];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -201,7 +209,11 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
   const int gw = p.gw, group = wcta / gw, wg = wcta - group * gw;
   const int role = (wg + group) % gw;   // 0 producer, 1 (E, X) tiles, 2 + jw: jets 2 jw, 2 jw + 1
   const int g = lane >> 2, q = lane & 3;
+#ifdef PB2_TRACE
+  const int m = p.m, ncw = gw - 1, nx = 32 * ncw, xbar = p.dry == 3 ? -1 : 1 + group;
+#else
   const int m = p.m, ncw = gw - 1, nx = 32 * ncw, xbar = 1 + group;
+#endif
 
   const uint32_t a_cG = smem_u32(u8_smem);
   const uint32_t a_grp = a_cG + 8u * (uint32_t)(p.o_grp + group * p.grp_stride);
@@ -473,7 +485,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
           tE[i4] *= cM;
           tX[i4] *= cM;
         }
-        bar_sync(xbar, nx);
+        U8_BAR(xbar, nx);
         int kq = M - 1;
         for (; kq >= 1; kq -= 2) {
           u8_step_ex<0, false>(tE, tX, bE2, bX2, A, iE, ypub, a_c + 8u * kq, xbar, nx);
@@ -632,7 +644,7 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
             bJ[a][i4] = t[a][i4];
             t[a][i4] *= cM;
           }
-        bar_sync(xbar, nx);
+        U8_BAR(xbar, nx);
         int kq = M - 1;
         for (; kq >= 1; kq -= 2) {
           u8_step_jets<W, 0, false, false>(t, bJ, A, ev, yad, a_c + 8u * kq, two, xbar, nx);
