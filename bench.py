@@ -408,6 +408,44 @@ def run_ours(args):
                      "kernel": "knot_objective_kernel (one CTA per knot, one launch for value and gradient)",
                      "note": "latency-bound at this size: the whole trajectory is %d KB" % (8 * p.D * p.K // 1024)}
         del go
+        # ---- one whole NLP iterate on the device: eval_g + eval_jac_g (dynamics and linear rows),
+        #      eval_f + eval_grad_f, eval_h, all reading the same resident trajectory ----
+        iterate = None
+        if hess is not None and p.D == p.n_x + 2 + 3 * p.m and p.x_off == 0:
+            traj_s = pb.NamedTrajectory.smooth_pulse_layout(Z, p.n_x, p.m, "U")
+            Lc = pb.B200KnotLinearConstraints(traj_s)
+            dLd = torch.empty(Lc.dim, dtype=torch.float64, device=dev)
+            dLv = torch.empty(Lc.nnz_jac, dtype=torch.float64, device=dev)
+            isteps = max(3, min(args.steps, 50))
+
+            def one_iterate(i, st_):
+                s_ = i % nsets
+                B.residual_jacobian_device(Zs[s_], outs[s_][:B.dim], outs[s_][B.dim:], st_)
+                Lc.residual_jacobian_device(Zs[s_], dLd, dLv, st_)
+                Jobj.value_gradient_device(Zs[s_], dJ, dG[i & 1], st_)
+                B.hessian_device(Zs[s_], dmu, dH[i & 1], st_)
+
+            for i in range(3):
+                one_iterate(i, stream.cuda_stream)
+            torch.cuda.synchronize()
+            gi = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gi, stream=stream):
+                is_ = torch.cuda.current_stream().cuda_stream
+                for i in range(isteps):
+                    one_iterate(i, is_)
+            gi.replay()
+            torch.cuda.synchronize()
+            ev[0].record()
+            gi.replay()
+            ev[1].record()
+            torch.cuda.synchronize()
+            it_ms = ev[0].elapsed_time(ev[1]) / isteps
+            iterate = {"ms_per_iterate": it_ms, "launches_per_iterate": 4,
+                       "calls": "residual+Jacobian (dynamics), residual+Jacobian (derivative pairs, time consistency), "
+                                "objective value+gradient, Lagrangian Hessian; one resident trajectory, one stream"}
+            del gi
+            Lc.close()
+        objective["nlp_iterate"] = iterate
         Jobj.close()
 
     # ---- end to end through the public host-pointer API (pinned host buffers, H2D + D2H) ----
