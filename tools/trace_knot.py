@@ -15,6 +15,14 @@ mode = os.environ.get("TRACE_MODE", "resjac")
 for _ in range(3):
     if mode == "hess":
         B.hessian_values(Z, _)  if False else B.hessian_values(Z, np.random.default_rng(0).standard_normal(B.dim))
+    elif os.environ.get("TRACE_DEVICE"):
+        # the benchmarked configuration: device-resident canonical outputs (not the compact host path)
+        import torch
+        dZ = torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda()
+        dd = torch.empty(B.dim, dtype=torch.float64, device="cuda")
+        dv = torch.empty(B.nnz_jac, dtype=torch.float64, device="cuda")
+        B.residual_jacobian_device(dZ, dd, dv, None)
+        torch.cuda.synchronize()
     else:
         B.residual_jacobian(Z)
 out = np.zeros(8 * 16 * 8, dtype=np.int64)
