@@ -7,6 +7,13 @@ buffer (no pack kernel), then a single in-place ``all_gather_into_tensor`` (NCCL
 NVLink/NVSwitch on the GPU box; gloo in the CPU plumbing tests) assembles the full arrays on
 every rank.  COO structure is computed redundantly per rank (no communication).
 
+For the 3-qubit unitary shape the exchange is fused into the kernel: the record buffer lives in
+symmetric memory (mapped into every rank over NVLink), each finished knot's compact record is
+stored by the producing kernel straight into every rank's buffer, and the only collective left is
+the symmetric-memory barrier; every rank then expands all records locally.  ``fused="auto"`` uses
+it whenever the mapping can be set up on all ranks and falls back to the NCCL all-gather of the
+records otherwise (a transport choice; both run the same CUDA kernels).
+
 The reference has no distributed code at all; this is the new exchange
 step the north star asks for.
 """
@@ -29,7 +36,7 @@ class ShardedBilinearIntegrator:
     """
 
     def __init__(self, kind, G_drift, G_drives, *, K, D, x_off, dt_off, u_off, rank, world,
-                 device=0, group=None, tensor_device=None, make_local=None, algorithm="auto"):
+                 device=0, group=None, tensor_device=None, make_local=None, algorithm="auto", fused="auto"):
         import torch
         self.torch = torch
         self.K, self.D = K, D
@@ -59,8 +66,38 @@ class ShardedBilinearIntegrator:
         # compact records (include/piccolo_b200.h): when the local evaluator offers them, the records
         # are what crosses NVLink and the canonical arrays are rebuilt locally after the gather
         self.cs = int(getattr(self.local, "compact_stride", 0)) if str(self.tensor_device).startswith("cuda") else 0
+        self.fused, self._symm, self._peer_ptrs = False, None, None
         if self.cs:
             self.comp = torch.zeros(max(1, self.cs * self.per * world), dtype=torch.float64, device=self.tensor_device)
+            if world > 1 and fused in ("auto", True):
+                self._setup_fused(device, required=fused is True)
+
+    def _setup_fused(self, device, required):
+        """Re-home the record buffer in symmetric memory and map every rank's copy (NVLink peer memory)."""
+        torch = self.torch
+        dist = torch.distributed
+        ok = True
+        try:
+            from . import capi
+            lib = capi.load_library()
+            for r in range(torch.cuda.device_count()):
+                if r != device:
+                    lib.pb2_enable_peer_access(device, r)      # best effort: symmetric memory maps via cuMem anyway
+            import torch.distributed._symmetric_memory as symm_mem
+            t = symm_mem.empty(self.comp.numel(), dtype=torch.float64, device=self.tensor_device)
+            t.zero_()
+            hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            self.comp, self._symm = t, hdl
+            self._peer_ptrs = [int(x) for x in hdl.buffer_ptrs]
+        except Exception as e:                                  # no peer mapping on this rank
+            if required:
+                raise
+            ok, self._why_not_fused = False, repr(e)
+        flag = torch.tensor([1 if ok else 0], device=self.tensor_device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self.fused = bool(flag.item())
+        if required and not self.fused:
+            raise RuntimeError("fused exchange could not be set up on every rank")
 
     # views into the gather buffer ---------------------------------------------------------
     def _slot(self, r):
@@ -82,10 +119,17 @@ class ShardedBilinearIntegrator:
         if Z_host is not None:
             slab = np.ascontiguousarray(self.local_columns(np.asarray(Z_host)).T).reshape(-1)
             self.zslab.copy_(torch.from_numpy(slab), non_blocking=True)
+        if self.fused:
+            # nobody may still be expanding the previous call's records when new ones arrive
+            # (every rank takes part, also one that owns no knots)
+            self._symm.barrier(channel=1)
         if self.n_local > 0:
             if self.zslab.is_cuda:
                 st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-                if self.cs:
+                if self.fused:
+                    self.local.residual_jacobian_exchange_device(self.zslab, self.rank, self._peer_ptrs,
+                                                                 self.rank * self.cs * self.per, st)
+                elif self.cs:
                     mine = self.comp[self.rank * self.cs * self.per:(self.rank + 1) * self.cs * self.per]
                     self.local.residual_jacobian_compact_device(self.zslab, mine, st)
                 else:
@@ -100,7 +144,9 @@ class ShardedBilinearIntegrator:
         if self.cs:
             torch = self.torch
             mine = self.comp[self.rank * self.cs * self.per:(self.rank + 1) * self.cs * self.per]
-            if self.world > 1:
+            if self.fused:
+                self._symm.barrier(channel=0)     # every rank's records have landed everywhere
+            elif self.world > 1:
                 torch.distributed.all_gather_into_tensor(self.comp, mine, group=self.group)
             st = torch.cuda.current_stream().cuda_stream
             for r in range(self.world):       # every rank slot holds `per` records (the last may be ragged)

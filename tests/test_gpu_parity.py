@@ -813,3 +813,18 @@ def test_fused_multi_ket_integrator_matches_per_state_integrators():
     with pytest.raises(ValueError):
         pb.B200BilinearIntegrator("unitary", p3.G0, list(p3.Gj), K=p3.K, D=p3.D, x_off=0, dt_off=p3.dt_off,
                                   u_off=p3.u_off, n_states=2)
+
+
+def test_sharded_integrator_two_gpus_fused_exchange():
+    """Two ranks, one per GPU: the fused NVLink exchange and the NCCL all-gather of the records both
+    reproduce the single-GPU arrays bitwise on every rank (skipped on a one-GPU box)."""
+    import os, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "sharded_check.py")],
+                       capture_output=True, text=True, timeout=240, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout
