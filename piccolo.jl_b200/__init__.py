@@ -9,6 +9,7 @@ integrator plug-in interface for this path only:
     evaluate!(delta, B, traj)      integrators.jl:311                 evaluate_(delta, B, traj)
     eval_jacobian(B, traj)         integrators.jl:780-782             eval_jacobian(B, traj)
     jacobian_structure / hessian_structure   test/aqua.jl:6-9         same names
+    test_integrator(B, traj; atol)  integrators.jl:359                test_integrator(B, traj, atol=)
     B.dim, B.x_dim, B.x_name       integrators.jl:307-309,552         same fields
     *InfidelityObjective, LeakageObjective, QuadraticRegularizer      objectives.py (src/control/objectives.jl)
 
@@ -24,7 +25,7 @@ from .generators import (  # noqa: F401
 from .integrators import (  # noqa: F401
     B200BilinearIntegrator, B200KnotLinearConstraints, BilinearIntegrator, DensityTrajectory, KetTrajectory,
     MultiKetTrajectory, NamedTrajectory, OpenQuantumSystem, QuantumSystem, SamplingTrajectory, UnitaryTrajectory,
-    eval_jacobian, evaluate_, hessian_of_lagrangian, hessian_structure, jacobian_structure,
+    eval_jacobian, evaluate_, hessian_of_lagrangian, hessian_structure, jacobian_structure, test_integrator,
 )
 from .objectives import (  # noqa: F401
     B200Objective, CoherentKetInfidelityObjective, DensityMatrixInfidelityObjective,

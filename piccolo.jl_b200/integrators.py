@@ -431,3 +431,65 @@ def hessian_of_lagrangian(B, traj, mu):
     vals = B.hessian_values(traj, mu)
     n = B.D * B.K + B.global_dim
     return sp.coo_matrix((vals, (rows - 1, cols - 1)), shape=(n, n))
+
+
+def test_integrator(B, traj, atol=1e-3, h=1e-5, seed=0):
+    """DirectTrajOpt's acceptance test for an integrator, as the reference calls it
+    (``test_integrator(integrator, traj; atol = 1e-3)``, integrators.jl:359 and the dispatch test items
+    after it): the analytic Jacobian and the Hessian of the Lagrangian must agree with derivatives of
+    the integrator's own residual.  DirectTrajOpt differentiates with ForwardDiff; here every
+    evaluation is the CUDA path itself and the derivatives are central differences of it (step ``h``),
+    so the check needs no second implementation.  Raises AssertionError with the worst entry."""
+    Z0 = np.asfortranarray(traj.data if isinstance(traj, NamedTrajectory) else traj, dtype=np.float64)
+    D, K = Z0.shape
+    n = D * K
+    rows, cols = B.jacobian_structure()
+    vals = B.jacobian_values(Z0)
+    J = np.zeros((B.dim, n))
+    np.add.at(J, (rows - 1, cols - 1), vals)
+
+    def residual(z):
+        out = np.empty(B.dim)
+        B.evaluate_(out, z.reshape(D, K, order="F"))
+        return out
+
+    z0 = Z0.reshape(-1, order="F")
+    touched = np.unique(cols - 1)
+    Jfd = np.zeros_like(J)
+    for c in touched:
+        e = np.zeros(n)
+        e[c] = h
+        Jfd[:, c] = (residual(z0 + e) - residual(z0 - e)) / (2 * h)
+    err = np.abs(J - Jfd)
+    assert err.max() <= atol, f"Jacobian differs from finite differences by {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+    # columns the structure does not mention must not influence the residual
+    rest = np.setdiff1d(np.arange(n), touched)
+    if rest.size:
+        e = np.zeros(n)
+        e[rest] = h
+        assert np.abs(residual(z0 + e) - residual(z0)).max() <= atol * h
+
+    mu = np.random.default_rng(seed).standard_normal(B.dim)
+    hr, hc = B.hessian_structure()
+    hv = B.hessian_values(Z0, mu)
+    H = np.zeros((n, n))
+    np.add.at(H, (hr - 1, hc - 1), hv)
+    H = H + np.triu(H, 1).T                      # upper triangle -> symmetric
+
+    def grad(z):                                 # J(z)^T mu through the analytic Jacobian values
+        g = np.zeros(n)
+        np.add.at(g, cols - 1, B.jacobian_values(z.reshape(D, K, order="F")) * mu[rows - 1])
+        return g
+
+    Hfd = np.zeros((n, n))
+    for c in touched:
+        e = np.zeros(n)
+        e[c] = h
+        Hfd[:, c] = (grad(z0 + e) - grad(z0 - e)) / (2 * h)
+    err = np.abs(H - Hfd)
+    assert err.max() <= atol * max(1.0, np.abs(mu).max()), \
+        f"Hessian of the Lagrangian differs from finite differences by {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+    return True
+
+
+test_integrator.__test__ = False   # not a pytest item

@@ -828,3 +828,88 @@ def test_sharded_integrator_two_gpus_fused_exchange():
                        capture_output=True, text=True, timeout=240, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MISMATCH" not in r.stdout
+
+
+# ---- the reference's own integrator acceptance tests (integrators.jl:345-560), through the CUDA path --------
+def _zero_control_traj(state_names, n_x_each, m, N=11, seed=0, zero_controls=True):
+    """NamedTrajectory(qtraj, 11) stand-in: zero controls on a uniform 0..1 time grid as in the reference's
+    test items (the derivative check does not need a feasible trajectory, so states are random)."""
+    rng = np.random.default_rng(seed)
+    D = len(state_names) * n_x_each + 2 + 3 * m
+    Z = np.zeros((D, N))
+    Z[:len(state_names) * n_x_each] = 0.5 * rng.standard_normal((len(state_names) * n_x_each, N))
+    o = len(state_names) * n_x_each
+    Z[o] = 0.1
+    Z[o + 1] = np.linspace(0.0, 1.0, N)
+    if not zero_controls:
+        Z[o + 2:o + 2 + m] = 0.7 * rng.standard_normal((m, N))
+    if len(state_names) == 1:
+        return pb.NamedTrajectory.smooth_pulse_layout(Z, n_x_each, m, state_names[0])
+    return pb.NamedTrajectory.multi_state_layout(Z, state_names, n_x_each, m)
+
+
+@pytest.mark.parametrize("zero_controls", [True, False])
+def test_reference_dispatch_test_items(zero_controls):
+    X, Y, Zp = np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1.0, -1.0])
+    sys_ = pb.QuantumSystem(Zp, [X, Y], [1.0, 1.0])
+    # "BilinearIntegrator dispatch on UnitaryTrajectory" (integrators.jl:345-363)
+    qtraj = pb.UnitaryTrajectory(sys_)
+    traj = _zero_control_traj([qtraj.state_name], 8, 2, zero_controls=zero_controls)
+    B = pb.BilinearIntegrator(qtraj, 11, traj)
+    assert isinstance(B, pb.B200BilinearIntegrator) and B.x_dim == 8 and B.dim == 8 * 10
+    assert pb.test_integrator(B, traj, atol=1e-3)
+    B.close()
+    # "... on KetTrajectory" (:365-383)
+    qtraj = pb.KetTrajectory(sys_)
+    traj = _zero_control_traj([qtraj.state_name], 4, 2, zero_controls=zero_controls)
+    B = pb.BilinearIntegrator(qtraj, 11, traj)
+    assert B.x_dim == 4
+    assert pb.test_integrator(B, traj, atol=1e-3)
+    B.close()
+    # "... on DensityTrajectory" (:385-413): sigma-minus decay, compact iso => x_dim = n^2
+    L = np.array([[0.0, 0.1], [0.0, 0.0]], dtype=complex)
+    osys = pb.OpenQuantumSystem(Zp, [X], [1.0], dissipation_operators=[L])
+    qtraj = pb.DensityTrajectory(osys)
+    traj = _zero_control_traj([qtraj.state_name], 4, 1, zero_controls=zero_controls)
+    B = pb.BilinearIntegrator(qtraj, 11, traj)
+    assert B.x_dim == osys.levels ** 2
+    assert pb.test_integrator(B, traj, atol=1e-3)
+    B.close()
+    # "... on SamplingTrajectory (Unitary)" / "(Ket)" (:415-480): one integrator per member, shared controls
+    members = [sys_, pb.QuantumSystem(1.1 * Zp, [X, Y], [1.0, 1.0])]
+    for base, n_x in ((pb.UnitaryTrajectory, 8), (pb.KetTrajectory, 4)):
+        st = pb.SamplingTrajectory(base, members)
+        traj = _zero_control_traj(st.state_names, n_x, 2, zero_controls=zero_controls)
+        Bs = pb.BilinearIntegrator(st, 11, traj)
+        assert isinstance(Bs, list) and len(Bs) == 2
+        for B in Bs:
+            assert pb.test_integrator(B, traj, atol=1e-3)
+            B.close()
+    # MultiKetTrajectory (:102-117): vector of integrators, and the fused single-launch form
+    mk = pb.MultiKetTrajectory(sys_, 2)
+    traj = _zero_control_traj(mk.state_names, 4, 2, zero_controls=zero_controls)
+    for B in pb.BilinearIntegrator(mk, 11, traj):
+        assert pb.test_integrator(B, traj, atol=1e-3)
+        B.close()
+    F = pb.BilinearIntegrator(mk, 11, traj, fused=True)
+    assert pb.test_integrator(F, traj, atol=1e-3)
+    F.close()
+
+
+def test_test_integrator_catches_a_wrong_jacobian(monkeypatch):
+    """The acceptance test must fail when the analytic values are off."""
+    X, Y, Zp = np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1.0, -1.0])
+    qtraj = pb.KetTrajectory(pb.QuantumSystem(Zp, [X, Y], [1.0, 1.0]))
+    traj = _zero_control_traj([qtraj.state_name], 4, 2, zero_controls=False)
+    B = pb.BilinearIntegrator(qtraj, 11, traj)
+    good = B.jacobian_values
+
+    def bad(Z, out=None):
+        v = good(Z, out)
+        v[3] += 0.01
+        return v
+
+    monkeypatch.setattr(B, "jacobian_values", bad)
+    with pytest.raises(AssertionError):
+        pb.test_integrator(B, traj, atol=1e-3)
+    B.close()
