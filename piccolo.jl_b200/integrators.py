@@ -123,13 +123,34 @@ class MultiKetTrajectory(_QTraj):
         self.state_names = [f"ψ̃{i + 1}" for i in range(n_states)]
 
 
-class SamplingTrajectory:
-    """An ensemble of systems sharing the controls: one integrator per member, each with its own
-    generator (integrators.jl:134-226; sampling_trajectory.jl:97-126, 306-349)."""
+class MultiDensityTrajectory(_QTraj):
+    """Several density matrices driven by one open system (compact iso each): one integrator per state."""
+    kind = "density"
 
-    def __init__(self, base_qtraj_type, systems):
-        self.kind, self.systems = base_qtraj_type.kind, list(systems)
-        self.state_names = [f"{base_qtraj_type.state_name}{i + 1}" for i in range(len(self.systems))]
+    def __init__(self, system, n_states):
+        super().__init__(system)
+        self.state_names = [f"ρ⃗̃{i + 1}" for i in range(n_states)]
+
+
+class SamplingTrajectory:
+    """An ensemble of systems sharing the controls: one integrator per member and state, each member
+    with its own generator (integrators.jl:134-226).  State components are named ``<base>1 .. <base>n``,
+    member-major for multi-state bases: member i owns names[(i-1)K .. iK) with K the number of states of
+    the base trajectory (sampling_trajectory.jl:97-126, 306-349).  ``base`` is a trajectory type
+    (single state) or an instance (``SamplingTrajectory(base_qtraj, systems)`` as in the reference)."""
+
+    def __init__(self, base, systems):
+        self.kind, self.systems = base.kind, list(systems)
+        multi = isinstance(base, (MultiKetTrajectory, MultiDensityTrajectory))
+        self.n_substates = len(base.state_names) if multi else 1
+        stem = (base.state_names[0][:-1] if multi else base.state_name)
+        n = len(self.systems) * self.n_substates
+        self.state_names = [f"{stem}{i + 1}" for i in range(n)]
+
+    def member_states(self):
+        """sampling_member_states: the state names of each member (lists of K names)."""
+        K = self.n_substates
+        return [self.state_names[i * K:(i + 1) * K] for i in range(len(self.systems))]
 
 
 # ----------------------------------------------------------------------------- #
@@ -365,20 +386,32 @@ def BilinearIntegrator(qtraj, traj_or_N, traj=None, **kw):
         # every state of a MultiKetTrajectory obeys the same generator and the blocks are contiguous in
         # the knot column, so one integrator (one launch) can evaluate them all: rows are knot-major,
         # state-major inside a knot (the per-state vector below is state-major, knot-major inside)
-        if not isinstance(qtraj, MultiKetTrajectory) or traj is None:
-            raise TypeError("fused=True needs a MultiKetTrajectory and its NamedTrajectory")
+        multi = isinstance(qtraj, (MultiKetTrajectory, MultiDensityTrajectory))
+        ensemble = isinstance(qtraj, SamplingTrajectory) and qtraj.n_substates > 1
+        if not (multi or ensemble) or traj is None:
+            raise TypeError("fused=True needs a multi-state trajectory (or an ensemble of them) and its NamedTrajectory")
         comps = traj.components
-        blocks = [comps[n] for n in qtraj.state_names]
-        if any(b.start != a.stop for a, b in zip(blocks, blocks[1:])) or len({len(b) for b in blocks}) != 1:
-            raise ValueError("state blocks must be contiguous and equally sized")
-        G0, Gj = qtraj.system.G_parts()
-        return B200BilinearIntegrator(
-            qtraj.kind, G0, Gj, K=traj.N, D=traj.dim, x_off=blocks[0].start, dt_off=comps[traj.timestep].start,
-            u_off=comps["u"].start, x_name="+".join(qtraj.state_names), global_dim=traj.global_dim,
-            n_states=len(blocks), **kw)
-    if isinstance(qtraj, (MultiKetTrajectory, SamplingTrajectory)) and traj is not None:
-        # a vector of integrators, one per state block, all reading the same Δt / u rows
-        systems = qtraj.systems if isinstance(qtraj, SamplingTrajectory) else [qtraj.system] * len(qtraj.state_names)
+
+        def fuse(names, sys_):
+            blocks = [comps[n] for n in names]
+            if any(b.start != a.stop for a, b in zip(blocks, blocks[1:])) or len({len(b) for b in blocks}) != 1:
+                raise ValueError("state blocks must be contiguous and equally sized")
+            G0, Gj = sys_.G_parts()
+            return B200BilinearIntegrator(
+                qtraj.kind, G0, Gj, K=traj.N, D=traj.dim, x_off=blocks[0].start, dt_off=comps[traj.timestep].start,
+                u_off=comps["u"].start, x_name="+".join(names), global_dim=traj.global_dim,
+                n_states=len(blocks), **kw)
+
+        if multi:
+            return fuse(qtraj.state_names, qtraj.system)
+        return [fuse(names, sys_) for names, sys_ in zip(qtraj.member_states(), qtraj.systems)]   # one per member
+    if isinstance(qtraj, (MultiKetTrajectory, MultiDensityTrajectory, SamplingTrajectory)) and traj is not None:
+        # a vector of integrators, one per state block (member-major for ensembles of multi-state
+        # trajectories), all reading the same Δt / u rows
+        if isinstance(qtraj, SamplingTrajectory):
+            systems = [s_ for s_ in qtraj.systems for _ in range(qtraj.n_substates)]
+        else:
+            systems = [qtraj.system] * len(qtraj.state_names)
         comps = traj.components
         out = []
         for name, sys_ in zip(qtraj.state_names, systems):

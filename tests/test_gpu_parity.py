@@ -913,3 +913,78 @@ def test_test_integrator_catches_a_wrong_jacobian(monkeypatch):
     with pytest.raises(AssertionError):
         pb.test_integrator(B, traj, atol=1e-3)
     B.close()
+
+
+def test_reference_sampling_ensemble_test_items():
+    """integrators.jl:482-560: sampling over density / multi-ket / multi-density bases."""
+    X, Y, Zp = np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1.0, -1.0])
+    # "SamplingTrajectory (Density)" (:482-526): compact Lindbladian per member, x_dim = n^2, and the
+    # member-1 integrator agrees with the plain density integrator of the same system
+    L = np.array([[0.0, 0.1], [0.0, 0.0]], dtype=complex)
+    o1 = pb.OpenQuantumSystem(Zp, [X], [1.0], dissipation_operators=[L])
+    o2 = pb.OpenQuantumSystem(0.95 * Zp, [X], [1.0], dissipation_operators=[L])
+    base = pb.DensityTrajectory(o1)
+    st = pb.SamplingTrajectory(base, [o1, o2])
+    traj = _zero_control_traj(st.state_names, 4, 1, zero_controls=False)
+    Bs = pb.BilinearIntegrator(st, 11, traj)
+    assert isinstance(Bs, list) and len(Bs) == 2
+    for B in Bs:
+        assert B.x_dim == o1.levels ** 2
+        assert pb.test_integrator(B, traj, atol=1e-3)
+    # parity pin (:518-525): same (x_next, x, u, dt) through member 1 and through the plain integrator
+    rng = np.random.default_rng(8)
+    x, x_next, u, dt = rng.standard_normal(4), rng.standard_normal(4), 0.3, 0.05
+    Zs = traj.data.copy(order="F")
+    c = traj.components
+    Zs[c["ρ⃗̃1"].start:c["ρ⃗̃1"].stop, 0], Zs[c["ρ⃗̃1"].start:c["ρ⃗̃1"].stop, 1] = x, x_next
+    Zs[c["Δt"].start, 0], Zs[c["u"].start, 0] = dt, u
+    d_member = np.empty(Bs[0].dim)
+    Bs[0].evaluate_(d_member, Zs)
+    tp = _zero_control_traj([base.state_name], 4, 1)
+    Zp_ = tp.data.copy(order="F")
+    Zp_[0:4, 0], Zp_[0:4, 1], Zp_[4, 0], Zp_[6, 0] = x, x_next, dt, u
+    ref = pb.BilinearIntegrator(base, 11, tp)
+    d_ref = np.empty(ref.dim)
+    ref.evaluate_(d_ref, Zp_)
+    assert np.allclose(d_member[:4], d_ref[:4], rtol=0, atol=1e-15)
+    ref.close()
+    for B in Bs:
+        B.close()
+    # "SamplingTrajectory (MultiKet)" (:528-556): 2 members x 2 kets = 4 integrators, names member-major
+    s1, s2 = pb.QuantumSystem(Zp, [X, Y], [1.0, 1.0]), pb.QuantumSystem(1.1 * Zp, [X, Y], [1.0, 1.0])
+    st = pb.SamplingTrajectory(pb.MultiKetTrajectory(s1, 2), [s1, s2])
+    traj = _zero_control_traj(st.state_names, 4, 2, zero_controls=False)
+    Bs = pb.BilinearIntegrator(st, 11, traj)
+    assert len(Bs) == 4 and [B.x_name for B in Bs] == ["ψ̃1", "ψ̃2", "ψ̃3", "ψ̃4"]
+    per_state = []
+    for B in Bs:
+        assert pb.test_integrator(B, traj, atol=1e-3)
+        per_state.append(B.residual_jacobian(traj.data)[0])
+        B.close()
+    # fused: one launch per member evaluates both of its kets; member 2 uses its own drift
+    Fs = pb.BilinearIntegrator(st, 11, traj, fused=True)
+    assert len(Fs) == 2 and [F.n_b for F in Fs] == [2, 2]
+    for i, F in enumerate(Fs):
+        assert pb.test_integrator(F, traj, atol=1e-3)
+        d = F.residual_jacobian(traj.data)[0].reshape(10, 2, 4)
+        assert np.abs(d[:, 0].reshape(-1) - per_state[2 * i]).max() < 1e-14
+        assert np.abs(d[:, 1].reshape(-1) - per_state[2 * i + 1]).max() < 1e-14
+        F.close()
+    # "SamplingTrajectory (MultiDensity)": one compact-Lindbladian integrator per (member, density)
+    st = pb.SamplingTrajectory(pb.MultiDensityTrajectory(o1, 2), [o1, o2])
+    traj = _zero_control_traj(st.state_names, 4, 1, zero_controls=False)
+    Bs = pb.BilinearIntegrator(st, 11, traj)
+    assert len(Bs) == 4 and all(B.x_dim == 4 for B in Bs)
+    for B in Bs:
+        assert pb.test_integrator(B, traj, atol=1e-3)
+        B.close()
+    # Jacobian shape pin (:780-782): dim x (traj.dim * traj.N + traj.global_dim)
+    qtraj = pb.KetTrajectory(s1)
+    traj = _zero_control_traj([qtraj.state_name], 4, 2, zero_controls=False)
+    B = pb.BilinearIntegrator(qtraj, 11, traj)
+    d = np.zeros(B.dim)
+    pb.evaluate_(d, B, traj)
+    assert not np.all(d == 0)
+    Jm = pb.eval_jacobian(B, traj)
+    assert Jm.shape == (B.dim, traj.dim * traj.N + traj.global_dim)
+    B.close()
