@@ -99,6 +99,18 @@ __device__ __forceinline__ void u8_mma(double (&d)[2][2], const double (&t)[4], 
   }
 }
 
+// d <- d + G t: the accumulators arrive pre-loaded with everything else the Horner step adds, so that
+// no FP64 CUDA-core instruction sits between two steps' tensor instructions.  (A dependent DFMA / DADD
+// issued while other warps of the sub-partition have DMMAs queued waits for the whole backlog: 265
+// cycles per busy warp measured with tools/dfma_lat.cu, against 8.5 on an idle pipe.)
+__device__ __forceinline__ void u8_mma_acc(double (&d)[2][2], const double (&t)[4], const double (&A)[4][2]) {
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) {
+    dmma884(d[0], t[kt], A[kt][0]);
+    dmma884(d[1], t[kt], A[kt][1]);
+  }
+}
+
 // G(u) = G0 + sum_j u_j G_j for this lane's 8 B-fragment slots (all loads first, then the arithmetic)
 template <bool LOWREG>
 __device__ __forceinline__ void u8_build_G(uint32_t a_z, uint32_t a_cG, int lane, int m, int u_off, double (&acc)[8]) {
@@ -141,39 +153,45 @@ __device__ __forceinline__ void u8_build_G(uint32_t a_z, uint32_t a_cG, int lane
     }
 }
 
-// ---- one Horner step of the (E, X) warp.  FIRST: first sub-step (B = unit columns for E) ------
+// ---- one Horner step of the (E, X) warp:  t <- c_k b + G t.  The caller keeps `acc` = c_k b for THIS
+// step (computed while the previous step's tensor instructions were in flight) and gets it back holding
+// c_{k-1} b for the next one; nothing but the publish and the barrier separates two steps' products.
+// FIRST: first sub-step (b_E = unit columns: the coefficient lands on one element, no arithmetic).
 template <int PAR, bool FIRST>
 __device__ __forceinline__ void u8_step_ex(double (&tE)[4], double (&tX)[4], const double (&bE)[4],
                                            const double (&bX)[4], const double (&A)[4][2], int iE, uint32_t ypub,
-                                           uint32_t ck_addr, int xbar, int nx) {
+                                           uint32_t ck_next_addr, int xbar, int nx, double (&accE)[4],
+                                           double (&accX)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) sts_f64<PAR * 1024>(ypub + i * 256, tX[i]);
-  const double ck = lds_f64<0>(ck_addr);
   double dE[2][2], dX[2][2];
-  u8_mma(dX, tX, A);
-  u8_mma(dE, tE, A);
-  U8_BAR(xbar, nx);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    tX[i] = fma(ck, bX[i], dX[i >> 1][i & 1]);
-    if (FIRST) tE[i] = (i == iE) ? dE[i >> 1][i & 1] + ck : dE[i >> 1][i & 1];
-    else tE[i] = fma(ck, bE[i], dE[i >> 1][i & 1]);
+    dX[i >> 1][i & 1] = accX[i];
+    dE[i >> 1][i & 1] = accE[i];
+  }
+  U8_BAR(xbar, nx);
+  u8_mma_acc(dX, tX, A);
+  u8_mma_acc(dE, tE, A);
+  // the next step's additive terms, queued behind the products just issued
+  const double ckn = lds_f64<0>(ck_next_addr);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    accX[i] = ckn * bX[i];
+    if (FIRST) accE[i] = (i == iE) ? ckn : 0.0;
+    else accE[i] = ckn * bE[i];
+    tX[i] = dX[i >> 1][i & 1];
+    tE[i] = dE[i >> 1][i & 1];
   }
 }
 
-// ---- one Horner step of a jet warp (two jet tiles).  FIRST: B_j = 0; NOMMA: the iterate is zero --
+// ---- one Horner step of a jet warp (two jet tiles):  t <- c_k b + G t + G_j y,  y the state iterate
+// the (E, X) warp published for this step.  The coupling term (and c_k b) is formed first and handed
+// to the tensor instructions as their accumulator.  FIRST: B_j = 0; NOMMA: the iterate is zero.
 template <int W, int PAR, bool FIRST, bool NOMMA>
 __device__ __forceinline__ void u8_step_jets(double (&t)[2][4], const double (&bJ)[2][4], const double (&A)[4][2],
                                              const double (&ev)[2][4][W], const uint32_t (&yad)[2][4][W],
                                              uint32_t ck_addr, bool two, int xbar, int nx) {
-  double d[2][2][2];
-  if (NOMMA) {
-#pragma unroll
-    for (int a = 0; a < 2; ++a) d[a][0][0] = d[a][0][1] = d[a][1][0] = d[a][1][1] = 0.0;
-  } else {
-    u8_mma(d[0], t[0], A);
-    if (two) u8_mma(d[1], t[1], A);
-  }
   double ck = 0.0;
   if (!FIRST) ck = lds_f64<0>(ck_addr);
   U8_BAR(xbar, nx);
@@ -184,21 +202,31 @@ __device__ __forceinline__ void u8_step_jets(double (&t)[2][4], const double (&b
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int ww = 0; ww < W; ++ww) y[a][i][ww] = lds_f64<PAR * 1024>(yad[a][i][ww]);
+  double d[2][2][2];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double v = d[a][i >> 1][i & 1];
-      if (!FIRST) v = fma(ck, bJ[a][i], v);
+      double v = FIRST ? ev[a][i][0] * y[a][i][0] : fma(ev[a][i][0], y[a][i][0], ck * bJ[a][i]);
 #pragma unroll
-      for (int ww = 0; ww < W; ++ww) v = fma(ev[a][i][ww], y[a][i][ww], v);
-      t[a][i] = v;
+      for (int ww = 1; ww < W; ++ww) v = fma(ev[a][i][ww], y[a][i][ww], v);
+      d[a][i >> 1][i & 1] = v;
     }
+  if (!NOMMA) {
+    u8_mma_acc(d[0], t[0], A);
+    if (two) u8_mma_acc(d[1], t[1], A);
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[a][i] = d[a][i >> 1][i & 1];
 }
 
 #ifdef PB2_TRACE
 #define U8_STAMP(i) do { if (blockIdx.x == 0 && lane == 0 && i_knot < 4) p.trace[((wcta * 4 + i_knot) * 8) + (i)] = clock64(); } while (0)
+#define U8_STAMPX(i) do { if (blockIdx.x == 0 && lane == 0 && i_knot == 0) p.trace[((wcta * 4 + 3) * 8) + (i)] = clock64(); } while (0)
 #else
+#define U8_STAMPX(i) do { } while (0)
 #define U8_STAMP(i) do { } while (0)
 #endif
 
@@ -290,11 +318,13 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         U8_STAMP(1);
         // the first knot's G(u) is built by the compute warps themselves (they are idle anyway, and it
         // takes the hand-over off the start-up path); from then on this warp runs ahead of them
+        U8_STAMPX(0);
         double dt = lds_f64<0>(a_z + 8u * p.dt_off);
         double nrm = lds_f64<0>(a_cG + 8u * p.o_norm);
         for (int j = 0; j < m; ++j)
           nrm = fma(fabs(lds_f64<0>(a_z + 8u * (uint32_t)(p.u_off + j))),
                     lds_f64<0>(a_cG + 8u * (uint32_t)(p.o_norm + 1 + j)), nrm);
+        U8_STAMPX(1);
         if (i > 0) {
           double acc[8];
           u8_build_G<false>(a_z, a_cG, lane, m, p.u_off, acc);
@@ -315,17 +345,21 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
           }
         }
         // M = 1 + #{ l in 1..kMaxDeg-1 : theta_l < per }   (theta increasing; NaN -> M = 1)
+        U8_STAMPX(2);
         const unsigned below = __ballot_sync(0xffffffffu, lane >= 1 && lane < kMaxDeg && th_l < per);
         const int M = 1 + __popc(below);
+        U8_STAMPX(3);
         double pw = 1.0, sq = dt;   // dt^lane by binary powering
 #pragma unroll
         for (int bit = 0; bit < 5; ++bit) {
           if ((lane >> bit) & 1) pw *= sq;
           sq *= sq;
         }
+        U8_STAMPX(4);
         if (lane <= kMaxDeg) sts_f64<0>(a_p + 8u * 256u + 8u * lane, lane <= M ? if_l * pw : 0.0);
         if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a_p + 8u * 276u), "r"(M), "r"(n_sub) : "memory");
         __syncwarp();
+        U8_STAMPX(5);
         if (i == 0) {
           // groups that run in lockstep leave the tensor pipe idle, and flood L2 with their stores,
           // all at the same time: de-phase them.  A group with one knot less than its neighbours
@@ -466,13 +500,21 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
       // overtaken (this warp passes a knot's step barriers only together with them)
       const uint32_t ypub = ypub0 + (uint32_t)(i & 1) * 2048u;
       U8_STAMP(2);
+      double accE[4], accX[4];   // c_k b of the coming step
       {
         int kq = M - 1;
-        for (; kq >= 1; kq -= 2) {
-          u8_step_ex<0, true>(tE, tX, bX, bX, A, iE, ypub, a_c + 8u * kq, xbar, nx);
-          u8_step_ex<1, true>(tE, tX, bX, bX, A, iE, ypub, a_c + 8u * kq - 8u, xbar, nx);
+        const double c0 = lds_f64<0>(a_c + 8u * (uint32_t)kq);
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          accE[i4] = (i4 == iE) ? c0 : 0.0;
+          accX[i4] = c0 * bX[i4];
         }
-        if (kq == 0) u8_step_ex<0, true>(tE, tX, bX, bX, A, iE, ypub, a_c, xbar, nx);
+        // (a step asks for the coefficient after its own; the last one re-reads c_0, unused)
+        for (; kq >= 1; kq -= 2) {
+          u8_step_ex<0, true>(tE, tX, bX, bX, A, iE, ypub, a_c + 8u * kq - 8u, xbar, nx, accE, accX);
+          u8_step_ex<1, true>(tE, tX, bX, bX, A, iE, ypub, a_c + 8u * (uint32_t)(kq >= 2 ? kq - 2 : 0), xbar, nx, accE, accX);
+        }
+        if (kq == 0) u8_step_ex<0, true>(tE, tX, bX, bX, A, iE, ypub, a_c, xbar, nx, accE, accX);
       }
       // further sub-steps (||dt G|| beyond the largest tabulated radius: rare), general B
       for (int sub = 1; sub < n_sub; ++sub) {
@@ -487,11 +529,17 @@ __global__ void __launch_bounds__(kU8MaxThreads, 1) knot_u8_kernel(const __grid_
         }
         U8_BAR(xbar, nx);
         int kq = M - 1;
-        for (; kq >= 1; kq -= 2) {
-          u8_step_ex<0, false>(tE, tX, bE2, bX2, A, iE, ypub, a_c + 8u * kq, xbar, nx);
-          u8_step_ex<1, false>(tE, tX, bE2, bX2, A, iE, ypub, a_c + 8u * kq - 8u, xbar, nx);
+        const double c0 = lds_f64<0>(a_c + 8u * (uint32_t)kq);
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          accE[i4] = c0 * bE2[i4];
+          accX[i4] = c0 * bX2[i4];
         }
-        if (kq == 0) u8_step_ex<0, false>(tE, tX, bE2, bX2, A, iE, ypub, a_c, xbar, nx);
+        for (; kq >= 1; kq -= 2) {
+          u8_step_ex<0, false>(tE, tX, bE2, bX2, A, iE, ypub, a_c + 8u * kq - 8u, xbar, nx, accE, accX);
+          u8_step_ex<1, false>(tE, tX, bE2, bX2, A, iE, ypub, a_c + 8u * (uint32_t)(kq >= 2 ? kq - 2 : 0), xbar, nx, accE, accX);
+        }
+        if (kq == 0) u8_step_ex<0, false>(tE, tX, bE2, bX2, A, iE, ypub, a_c, xbar, nx, accE, accX);
       }
       // ---- d/d dt = -G(u) E x : one more generator product on the state tile --------------------
       U8_STAMP(3);

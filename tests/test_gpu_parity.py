@@ -18,6 +18,7 @@ from tests import golden_util as GU
 pytestmark = pytest.mark.gpu
 
 RES_TOL, JAC_TOL, HESS_RTOL = 1e-12, 1e-11, 1e-9
+PATH_TOL = 1e-13   # two kernels evaluating the same quantity (different summation order)
 
 
 def make(p, algorithm="auto", **kw):
@@ -33,11 +34,12 @@ def check_all(p, Z, mu, B, hess=True):
     d, v = B.residual_jacobian(Z)
     assert np.abs(d - KN.residual(p, Z)).max() < RES_TOL
     assert np.abs(v - KN.jacobian_values(p, Z)).max() < JAC_TOL
-    # separate entry points give the same numbers as the fused one
+    # separate entry points give the same numbers as the fused one (a residual-only call may run a
+    # different kernel than the fused call -- the 3-qubit shape does -- so: to rounding, not bitwise)
     d2 = np.empty(B.dim)
     B.evaluate_(d2, Z)
-    assert np.array_equal(d, d2)
-    assert np.array_equal(v, B.jacobian_values(Z))
+    assert np.abs(d - d2).max() < PATH_TOL
+    assert np.abs(v - B.jacobian_values(Z)).max() < PATH_TOL
     if hess:
         h = B.hessian_values(Z, mu)
         ho = KN.hessian_values(p, Z, mu)
@@ -288,7 +290,8 @@ def test_tensor_core_path_unaligned_outputs():
     assert dd.data_ptr() % 16 == 8
     B.residual_jacobian_device(dZ, dd, dv, None)
     torch.cuda.synchronize()
-    assert np.array_equal(dd.cpu().numpy(), d) and np.array_equal(dv.cpu().numpy(), v)
+    # (the aligned call above ran the warp-specialised kernel, this one the general tensor-core kernel)
+    assert np.abs(dd.cpu().numpy() - d).max() < PATH_TOL and np.abs(dv.cpu().numpy() - v).max() < PATH_TOL
     assert buf[0].item() == 0.0 and buf[1 + B.dim].item() == 0.0 and buf[-1].item() == 0.0
     B.close()
 
