@@ -69,7 +69,12 @@ __host__ __device__ inline U8hSlot u8h_tile(int t, int m) {
   return s;
 }
 
-// One Horner step of a warp's two tiles.  PAR: exchange-buffer half.
+// One Horner step of a warp's two tiles,  t <- c_k base +- G t + (coupling terms read from the
+// exchange buffers).  PAR: exchange-buffer half.  Everything but the product is formed first and handed
+// to the tensor instructions as their accumulator, so no FP64 CUDA-core instruction sits between two
+// steps' products (such an instruction waits for every DMMA other warps have queued on the
+// sub-partition: tools/dfma_lat.cu).  The sign of an adjoint tile (G^T = -G) goes onto the operand by
+// flipping its sign bit, an integer instruction.
 template <int W, int PAR>
 __device__ __forceinline__ void u8h_step(double (&t)[2][4], const double (&base)[2][4], const double (&A)[4][2],
                                          const double (&ev)[2][2][4][W], const uint32_t (&yad)[2][2][4][W],
@@ -82,25 +87,35 @@ __device__ __forceinline__ void u8h_step(double (&t)[2][4], const double (&base)
       for (int i = 0; i < 4; ++i) sts_f64<PAR * kU8hXchBytes>(pub[a] + i * 256, t[a][i]);
     }
   const double ck = lds_f64<0>(ck_addr);
+  bar_sync(1, nthreads);
   double d[2][2][2];
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
-    if (act[a] && s >= skip[a]) u8_mma(d[a], t[a], A);
-    else d[a][0][0] = d[a][0][1] = d[a][1][0] = d[a][1][1] = 0.0;
-  }
-  bar_sync(1, nthreads);
-#pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    if (!act[a]) continue;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      double v = fma(ck, base[a][i], sgn[a] * d[a][i >> 1][i & 1]);
+      double v = ck * base[a][i];
+      if (act[a]) {
 #pragma unroll
-      for (int term = 0; term < 2; ++term)
+        for (int term = 0; term < 2; ++term)
 #pragma unroll
-        for (int ww = 0; ww < W; ++ww)
-          v = fma(ev[a][term][i][ww], lds_f64<PAR * kU8hXchBytes>(yad[a][term][i][ww]), v);
-      t[a][i] = v;
+          for (int ww = 0; ww < W; ++ww)
+            v = fma(ev[a][term][i][ww], lds_f64<PAR * kU8hXchBytes>(yad[a][term][i][ww]), v);
+      }
+      d[a][i >> 1][i & 1] = v;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    if (act[a] && s >= skip[a]) {
+      const int flip = sgn[a] < 0.0 ? (int)0x80000000 : 0;
+      double tn[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tn[i] = __hiloint2double(__double2hiint(t[a][i]) ^ flip, __double2loint(t[a][i]));
+      u8_mma_acc(d[a], tn, A);
+    }
+    if (act[a]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) t[a][i] = d[a][i >> 1][i & 1];
     }
   }
 }
