@@ -114,3 +114,72 @@ def test_sharded_gather_world2_gloo(tmp_path, K):
     outs = [pr.communicate(timeout=240)[0].decode() for pr in procs]
     assert all(pr.returncode == 0 for pr in procs), outs
     assert "SHARD_OK" in outs[0]
+
+
+# ---- objective host logic: complex goals -> real coefficient vectors of the C ABI's term --------------
+def _term_value(term, z):
+    """The formula the CUDA kernel evaluates for one term (include/piccolo_b200.h), in NumPy."""
+    zz = z[term.rows]
+    f = lambda a: 0.0 if a is None else float(a @ zz)
+    F = term.scale * (f(term.a_re) ** 2 + f(term.a_im) ** 2 + (0.0 if term.a_sq is None else float(term.a_sq @ (zz * zz)))) \
+        + f(term.a_lin)
+    return term.Q[0] * (abs(1 - F) if term.flags & 1 else F)
+
+
+def test_objective_terms_reproduce_the_reference_losses():
+    """No GPU: the coefficient vectors the constructors hand to pb2_obj_create, evaluated with the
+    documented real-form formula, equal the complex-arithmetic restatement of objectives.jl."""
+    from oracle import objectives as OB
+    rng = np.random.default_rng(17)
+    cplx = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    # unitary (full operator and EmbeddedOperator subspace form), 3 levels
+    N, m, K = 3, 1, 4
+    Z = 0.5 * rng.standard_normal((2 * N * N + 2 + 3 * m, K))
+    traj = pb.NamedTrajectory.smooth_pulse_layout(Z, 2 * N * N, m, "Ũ⃗")
+    Ug = np.linalg.qr(cplx(N, N))[0]
+    J = pb.UnitaryInfidelityObjective(Ug, "Ũ⃗", traj, Q=100.0)
+    assert np.isclose(_term_value(J.terms[0], Z[:, -1]), OB.unitary_infidelity(Z[:2 * N * N, -1], Ug, 100.0)[0], rtol=1e-13)
+    Us = np.linalg.qr(cplx(2, 2))[0]
+    J = pb.UnitaryInfidelityObjective(Us, "Ũ⃗", traj, Q=30.0, subspace=[0, 2])
+    ref = OB.unitary_infidelity(Z[:2 * N * N, -1], Us, 30.0, subspace=[0, 2])[0]
+    assert np.isclose(_term_value(J.terms[0], Z[:, -1]), ref, rtol=1e-13)
+    # kets: single, coherent (weighted / uniform)
+    Zk = 0.5 * rng.standard_normal((2 * 4 + 2 + 3, K))
+    tk = pb.NamedTrajectory.multi_state_layout(Zk, ["ψ̃1", "ψ̃2"], 4, 1)
+    g1, g2 = cplx(2), cplx(2)
+    g1, g2 = g1 / np.linalg.norm(g1), g2 / np.linalg.norm(g2)
+    J = pb.KetInfidelityObjective(g2, "ψ̃2", tk, Q=7.0)
+    assert np.isclose(_term_value(J.terms[0], Zk[:, -1]), OB.ket_infidelity(Zk[4:8, -1], g2, 7.0)[0], rtol=1e-13)
+    for w in (None, [0.9, 0.1], [2.0, 2.0]):
+        J = pb.CoherentKetInfidelityObjective([g1, g2], ["ψ̃1", "ψ̃2"], tk, Q=100.0, weights=w)
+        ref = OB.coherent_ket_infidelity([Zk[0:4, -1], Zk[4:8, -1]], [g1, g2], 100.0, w)[0]
+        assert np.isclose(_term_value(J.terms[0], Zk[:, -1]), ref, rtol=1e-13)
+    # the reference's own expectation (objectives.jl:592): F = |0.9*1 + 0.1*1/2|^2
+    p0, p1 = np.array([1, 0], complex), np.array([0, 1], complex)
+    z = np.zeros(Zk.shape[0])
+    z[0:4], z[4:8] = np.concatenate([p1.real, p1.imag]), 0.5 * np.concatenate([p0.real, p0.imag])
+    J = pb.CoherentKetInfidelityObjective([p1, p0], ["ψ̃1", "ψ̃2"], tk, Q=100.0, weights=[0.9, 0.1])
+    assert np.isclose(_term_value(J.terms[0], z), 100.0 * (1 - 0.9025), rtol=1e-13)
+    with pytest.raises(ValueError):
+        pb.CoherentKetInfidelityObjective([p1, p0], ["ψ̃1"], tk)
+    # density matrices in the compact iso, leakage, composition
+    n = 3
+    Zd = 0.4 * rng.standard_normal((n * n + 2 + 3, K))
+    td = pb.NamedTrajectory.smooth_pulse_layout(Zd, n * n, 1, "ρ⃗̃")
+    A = cplx(n, n)
+    rho_g = A @ A.conj().T
+    rho_g /= np.trace(rho_g).real
+    psi = cplx(n)
+    psi /= np.linalg.norm(psi)
+    J1 = pb.DensityMatrixInfidelityObjective("ρ⃗̃", rho_g, td, Q=50.0)
+    J2 = pb.DensityMatrixPureStateInfidelityObjective("ρ⃗̃", psi, td, Q=5.0)
+    assert np.isclose(_term_value(J1.terms[0], Zd[:, -1]), OB.density_infidelity(Zd[:n * n, -1], rho_g, 50.0)[0], rtol=1e-13)
+    assert np.isclose(_term_value(J2.terms[0], Zd[:, -1]), OB.density_pure_state_infidelity(Zd[:n * n, -1], psi, 5.0)[0], rtol=1e-13)
+    JL = pb.LeakageObjective([1, 4], "ρ⃗̃", td, times=[0, 2], Qs=[1.0, 3.0])
+    t = JL.terms[0]
+    got = sum(q * t.scale * 0 + q * float(t.a_sq @ (Zd[t.rows, k] ** 2)) for k, q in zip(t.times, t.Q))
+    assert np.isclose(got, OB.leakage(Zd[:n * n][:, [0, 2]], [1, 4], [1.0, 3.0])[0], rtol=1e-13)
+    Jsum = J1 + J2 + JL + pb.QuadraticRegularizer("u", td, 0.1)
+    assert len(Jsum.terms) == 3 and len(Jsum.regs) == 1 and Jsum._h is None     # nothing touched the library yet
+    with pytest.raises(ValueError):
+        J1 + pb.KetInfidelityObjective(g1, "ψ̃1", tk)                           # different trajectory layouts
