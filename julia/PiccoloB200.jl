@@ -42,9 +42,11 @@ mutable struct B200BilinearIntegrator <: AbstractIntegrator
     nnz_hess::Int
     ncols::Int                    # traj.dim * traj.N + traj.global_dim   integrators.jl:780-782
     function B200BilinearIntegrator(kind, G0::Matrix{Float64}, Gj::Vector{Matrix{Float64}},
-                                    traj, x_name::Symbol, u_name::Symbol; device = 0)
+                                    traj, x_name::Symbol, u_name::Symbol; device = 0, n_states = 1)
         b = size(G0, 1)
-        n_b = kind == PB2_UNITARY ? b ÷ 2 : 1
+        # n_b contiguous state blocks share the generator: d columns of a unitary, or the n_states
+        # kets / densities of a multi-state trajectory fused into one integrator (x_name = the first)
+        n_b = kind == PB2_UNITARY ? b ÷ 2 : n_states
         Gjflat = isempty(Gj) ? zeros(1) : reduce(vcat, vec.(Gj))
         comps = traj.components
         desc = PB2Desc(kind, b, n_b, length(Gj), traj.N, traj.dim,
@@ -93,6 +95,33 @@ function Piccolo.BilinearIntegrator(qtraj::DensityTrajectory, traj::NamedTraject
     (sys.time_dependent || !linear_drives_only(sys)) && return BilinearIntegrator(qtraj, traj.N)
     G0, Gj = generator_parts(sys)
     B200BilinearIntegrator(PB2_DENSITY, G0, Gj, traj, Piccolo.state_name(qtraj), Piccolo.drive_name(qtraj))
+end
+
+# MultiKetTrajectory / SamplingTrajectory: a vector of integrators, one per state component, all reading
+# the same control rows (integrators.jl:102-117, 134-226) ...
+function Piccolo.BilinearIntegrator(qtraj::MultiKetTrajectory, traj::NamedTrajectory, ::Val{:b200}; fused = false)
+    sys = qtraj.system
+    (sys.time_dependent || !linear_drives_only(sys)) && return BilinearIntegrator(qtraj, traj.N)
+    G0, Gj = generator_parts(sys)
+    names = Piccolo.state_names(qtraj)
+    # ... or, since every ket obeys the same generator and the blocks are contiguous in the knot column,
+    # ONE integrator that evaluates them all in a single launch (rows knot-major, state-major inside a knot)
+    fused && return B200BilinearIntegrator(PB2_KET, G0, Gj, traj, names[1], Piccolo.drive_name(qtraj); n_states = length(names))
+    return [B200BilinearIntegrator(PB2_KET, G0, Gj, traj, nm, Piccolo.drive_name(qtraj)) for nm in names]
+end
+function Piccolo.BilinearIntegrator(qtraj::SamplingTrajectory, traj::NamedTrajectory, ::Val{:b200})
+    base = qtraj.base_trajectory
+    kind = base isa UnitaryTrajectory ? PB2_UNITARY : (base isa Union{KetTrajectory,MultiKetTrajectory} ? PB2_KET : PB2_DENSITY)
+    members = Piccolo.sampling_member_states(qtraj)          # Symbol or Vector{Symbol} per member (member-major)
+    out = AbstractIntegrator[]
+    for (sys, states) in zip(qtraj.systems, members)
+        (sys.time_dependent || !linear_drives_only(sys)) && return BilinearIntegrator(qtraj, traj.N)
+        G0, Gj = generator_parts(sys)
+        for nm in (states isa AbstractVector ? states : [states])
+            push!(out, B200BilinearIntegrator(kind, G0, Gj, traj, nm, Piccolo.drive_name(qtraj)))
+        end
+    end
+    return out
 end
 
 # ---- the AbstractIntegrator interface --------------------------------------------------------------
@@ -212,62 +241,162 @@ struct PB2ObjDesc
     device::Int32
 end
 
-mutable struct B200Objective <: DirectTrajOpt.Objectives.AbstractObjective
-    handle::Ptr{Cvoid}
-    n::Int                      # traj.dim * traj.N
+# Host-side description of a term / regularizer (kept alive by the objective; the library copies them
+# at pb2_obj_create).  Vectors are empty when absent.
+struct ObjTerm
+    flags::Int32
+    rows::Vector{Int32}                 # 0-based rows of the knot column
+    a_re::Vector{Float64}; a_im::Vector{Float64}; a_sq::Vector{Float64}; a_lin::Vector{Float64}
+    scale::Float64
+    times::Vector{Int32}                # 0-based knots; empty = terminal knot
+    Q::Vector{Float64}
+end
+struct ObjReg
+    rows::Vector{Int32}
+    R::Vector{Float64}
+    baseline::Matrix{Float64}           # rows × N, or 0 × 0
+    dt_power::Int32
+    times::Vector{Int32}                # empty = every knot
 end
 
-# ⟨goal|ψ⟩ for ψ̃ = [Re ψ; Im ψ]
-overlap_coeffs(g::AbstractVector{<:Complex}) = (vcat(real(g), imag(g)), vcat(-imag(g), real(g)))
+mutable struct B200Objective <: DirectTrajOpt.Objectives.AbstractObjective
+    terms::Vector{ObjTerm}
+    regs::Vector{ObjReg}
+    layout::NTuple{4,Int}               # (N, dim, 0-based Δt row, device)
+    handle::Ptr{Cvoid}                  # built on first use, so that `J1 + J2 + …` costs nothing
+end
+B200Objective(terms, regs, traj::NamedTrajectory; device = 0) =
+    B200Objective(terms, regs, (traj.N, traj.dim, first(traj.components[traj.timestep]) - 1, device), C_NULL)
 
-"""
-    B200UnitaryInfidelityObjective(U_goal, name, traj; Q, R = (u = 1e-2, ...), dt_power = 0)
+function Base.:+(a::B200Objective, b::B200Objective)
+    a.layout == b.layout || error("objectives were built on different trajectory layouts")
+    return B200Objective(vcat(a.terms, b.terms), vcat(a.regs, b.regs), a.layout, C_NULL)
+end
 
-`UnitaryInfidelityObjective(U_goal, name, traj; Q) + Σ QuadraticRegularizer(sym, traj, R[sym])`
-(smooth_pulse_problem.jl:240-250) as one device handle.
-"""
-function B200UnitaryInfidelityObjective(U_goal::AbstractMatrix{<:Complex}, name::Symbol, traj::NamedTrajectory;
-                                        Q = 100.0, R = NamedTuple(), dt_power = 0, device = 0)
-    n = size(U_goal, 1)
-    rows = Int32.(collect(traj.components[name]) .- 1)
-    a_re = zeros(length(rows)); a_im = zeros(length(rows))
-    for c = 1:n
-        r, i = overlap_coeffs(U_goal[:, c])
-        a_re[(2n*(c-1)+1):(2n*c)] = r
-        a_im[(2n*(c-1)+1):(2n*c)] = i
-    end
-    Qv = [Float64(Q)]
-    reg_rows = [Int32.(collect(traj.components[s]) .- 1) for s in keys(R)]
-    reg_R = [fill(Float64(R[s]), length(traj.components[s])) for s in keys(R)]
-    GC.@preserve rows a_re a_im Qv reg_rows reg_R begin
-        terms = [PB2ObjTerm(1, length(rows), pointer(rows), pointer(a_re), pointer(a_im), C_NULL, C_NULL,
-                            1 / n^2, 0, C_NULL, pointer(Qv))]
-        regs = [PB2ObjReg(length(reg_rows[i]), pointer(reg_rows[i]), pointer(reg_R[i]), C_NULL, dt_power, 0, C_NULL)
-                for i in eachindex(reg_rows)]
+ptr_or_null(v::Array) = isempty(v) ? Ptr{eltype(v)}(C_NULL) : pointer(v)
+
+function handle!(J::B200Objective)
+    J.handle == C_NULL || return J.handle
+    N, dim, dt_off, device = J.layout
+    GC.@preserve J begin
+        terms = [PB2ObjTerm(t.flags, length(t.rows), ptr_or_null(t.rows), ptr_or_null(t.a_re), ptr_or_null(t.a_im),
+                            ptr_or_null(t.a_sq), ptr_or_null(t.a_lin), t.scale, length(t.times), ptr_or_null(t.times),
+                            pointer(t.Q)) for t in J.terms]
+        regs = [PB2ObjReg(length(r.rows), ptr_or_null(r.rows), pointer(r.R), ptr_or_null(r.baseline), r.dt_power,
+                          length(r.times), ptr_or_null(r.times)) for r in J.regs]
         GC.@preserve terms regs begin
-            desc = PB2ObjDesc(traj.N, traj.dim, first(traj.components[traj.timestep]) - 1, 1, length(regs),
-                              pointer(terms), isempty(regs) ? C_NULL : pointer(regs), device)
+            desc = PB2ObjDesc(N, dim, dt_off, length(terms), length(regs), ptr_or_null(terms), ptr_or_null(regs), device)
             h = Ref{Ptr{Cvoid}}(C_NULL)
             check(ccall((:pb2_obj_create, LIB), Cint, (Ref{PB2ObjDesc}, Ref{Ptr{Cvoid}}), desc, h))
+            J.handle = h[]
         end
     end
-    J = B200Objective(h[], traj.dim * traj.N)
     finalizer(J -> ccall((:pb2_obj_destroy, LIB), Cvoid, (Ptr{Cvoid},), J.handle), J)
-    return J
+    return J.handle
+end
+
+rows0(traj, name) = Int32.(collect(traj.components[name]) .- 1)
+
+# ⟨goal|ψ⟩ for ψ̃ = [Re ψ; Im ψ]:  Re = a_re·ψ̃, Im = a_im·ψ̃
+overlap_coeffs(g::AbstractVector{<:Complex}) = (vcat(real(g), imag(g)), vcat(-imag(g), real(g)))
+const NOVEC, NOTIMES = Float64[], Int32[]
+const ONE_MINUS = Int32(1)
+
+"KetInfidelityObjective(ψ_goal, name, traj; Q)   src/control/objectives.jl:56-64"
+function B200KetInfidelityObjective(ψ_goal::AbstractVector{<:Complex}, name::Symbol, traj::NamedTrajectory; Q = 100.0, device = 0)
+    a_re, a_im = overlap_coeffs(ComplexF64.(ψ_goal))
+    return B200Objective([ObjTerm(ONE_MINUS, rows0(traj, name), a_re, a_im, NOVEC, NOVEC, 1.0, NOTIMES, [Float64(Q)])],
+                         ObjReg[], traj; device)
+end
+
+"CoherentKetInfidelityObjective(goals, names, traj; Q, weights)   objectives.jl:181-216 (weights normalised as :136-144)"
+function B200CoherentKetInfidelityObjective(ψ_goals, names::Vector{Symbol}, traj::NamedTrajectory;
+                                            Q = 100.0, weights = nothing, device = 0)
+    n = length(ψ_goals)
+    ws = Piccolo.QuantumObjectives.coherent_fidelity_weights(weights, n)
+    w = isnothing(ws) ? fill(1 / n, n) : ws
+    parts = [overlap_coeffs(ComplexF64.(g)) for g in ψ_goals]
+    rows = reduce(vcat, [rows0(traj, nm) for nm in names])
+    a_re = reduce(vcat, [w[i] .* parts[i][1] for i = 1:n])
+    a_im = reduce(vcat, [w[i] .* parts[i][2] for i = 1:n])
+    return B200Objective([ObjTerm(ONE_MINUS, rows, a_re, a_im, NOVEC, NOVEC, 1.0, NOTIMES, [Float64(Q)])], ObjReg[], traj; device)
+end
+
+"UnitaryInfidelityObjective(U_goal, name, traj; Q)   objectives.jl:330-337, 347-356"
+function B200UnitaryInfidelityObjective(U_goal::AbstractMatrix{<:Complex}, name::Symbol, traj::NamedTrajectory;
+                                        Q = 100.0, device = 0)
+    n = size(U_goal, 1)
+    parts = [overlap_coeffs(ComplexF64.(U_goal[:, c])) for c = 1:n]
+    a_re = reduce(vcat, first.(parts)); a_im = reduce(vcat, last.(parts))
+    return B200Objective([ObjTerm(ONE_MINUS, rows0(traj, name), a_re, a_im, NOVEC, NOVEC, 1 / n^2, NOTIMES, [Float64(Q)])],
+                         ObjReg[], traj; device)
+end
+
+"UnitaryInfidelityObjective(op::EmbeddedOperator, …)   objectives.jl:339-345 (unitary subspace goal)"
+function B200UnitaryInfidelityObjective(op::EmbeddedOperator, name::Symbol, traj::NamedTrajectory; Q = 100.0, device = 0)
+    Ug = ComplexF64.(unembed(op)); sub = op.subspace; n = length(sub)
+    Nl = isqrt(length(traj.components[name]) ÷ 2)
+    a_re = zeros(2Nl^2); a_im = zeros(2Nl^2); a_sq = zeros(2Nl^2)
+    for (p, c) in enumerate(sub), (q, i) in enumerate(sub)
+        g = Ug[q, p]; re = 2Nl * (c - 1) + i; im = re + Nl
+        a_re[re], a_re[im] = real(g), imag(g)
+        a_im[re], a_im[im] = -imag(g), real(g)
+        a_sq[re] = a_sq[im] = 1.0
+    end
+    return B200Objective([ObjTerm(ONE_MINUS, rows0(traj, name), a_re, a_im, a_sq, NOVEC, 1 / (n * (n + 1)), NOTIMES, [Float64(Q)])],
+                         ObjReg[], traj; device)
+end
+
+# Re tr(ρ W) = a·x for ρ = compact_iso_to_density(x)   (isomorphisms.jl:176-191 ordering)
+function compact_trace_coeffs(W::AbstractMatrix{<:Complex})
+    n = size(W, 1); a = Float64[]
+    for k = 1:n, j = 1:k
+        push!(a, j == k ? real(W[k, k]) : real(W[k, j] + W[j, k]))
+    end
+    for k = 2:n, j = 1:(k-1)
+        push!(a, imag(W[j, k] - W[k, j]))
+    end
+    return a
+end
+
+"DensityMatrixInfidelityObjective(name, ρ_goal, traj; Q)   objectives.jl:387-411"
+B200DensityMatrixInfidelityObjective(name::Symbol, ρ_goal::AbstractMatrix{<:Complex}, traj::NamedTrajectory; Q = 100.0, device = 0) =
+    B200Objective([ObjTerm(ONE_MINUS, rows0(traj, name), NOVEC, NOVEC, NOVEC, compact_trace_coeffs(ρ_goal), 1.0, NOTIMES, [Float64(Q)])],
+                  ObjReg[], traj; device)
+
+"DensityMatrixPureStateInfidelityObjective(name, ψ_goal, traj; Q)   objectives.jl:412-429"
+B200DensityMatrixPureStateInfidelityObjective(name::Symbol, ψ::AbstractVector{<:Complex}, traj::NamedTrajectory; Q = 100.0, device = 0) =
+    B200DensityMatrixInfidelityObjective(name, ψ * ψ', traj; Q, device)
+
+"LeakageObjective(indices, name, traj; times, Qs)   objectives.jl:464-474"
+function B200LeakageObjective(indices::AbstractVector{Int}, name::Symbol, traj::NamedTrajectory;
+                              times = 1:traj.N, Qs = fill(1.0, length(times)), device = 0)
+    rows = rows0(traj, name)[indices]
+    return B200Objective([ObjTerm(Int32(0), rows, NOVEC, NOVEC, fill(1 / length(indices), length(rows)), NOVEC, 1.0,
+                                  Int32.(collect(times) .- 1), Float64.(Qs))], ObjReg[], traj; device)
+end
+
+"QuadraticRegularizer(name, traj, R; baseline, times)  (DirectTrajOpt; Δt power: see include/piccolo_b200.h)"
+function B200QuadraticRegularizer(name::Symbol, traj::NamedTrajectory, R; baseline = zeros(0, 0), times = Int[],
+                                  dt_power = 0, device = 0)
+    rows = rows0(traj, name)
+    Rv = R isa Number ? fill(Float64(R), length(rows)) : Float64.(R)
+    return B200Objective(ObjTerm[], [ObjReg(rows, Rv, Matrix{Float64}(baseline), Int32(dt_power), Int32.(collect(times) .- 1))],
+                         traj; device)
 end
 
 function DirectTrajOpt.objective_value(J::B200Objective, traj::NamedTrajectory)
     v = Ref{Float64}(0.0)
     check(ccall((:pb2_obj_value_gradient, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Cint),
-                J.handle, traj.datavec, v, C_NULL, PB2_HOST))
+                handle!(J), traj.datavec, v, C_NULL, PB2_HOST))
     return v[]
 end
 
 function DirectTrajOpt.gradient!(∇::AbstractVector{Float64}, J::B200Objective, traj::NamedTrajectory)
     v = Ref{Float64}(0.0)
-    fill!(view(∇, (J.n+1):length(∇)), 0.0)          # global variables: no dependence
+    fill!(view(∇, (J.layout[1]*J.layout[2]+1):length(∇)), 0.0)          # global variables: no dependence
     check(ccall((:pb2_obj_value_gradient, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Cint),
-                J.handle, traj.datavec, v, ∇, PB2_HOST))
+                handle!(J), traj.datavec, v, ∇, PB2_HOST))
     return nothing
 end
 
