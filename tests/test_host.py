@@ -37,6 +37,18 @@ def test_no_cpu_fallback():
         pb.B200BilinearIntegrator("ket", np.zeros((4, 4)), [np.zeros((4, 4))], K=5, D=10,
                                   x_off=0, dt_off=4, u_off=6)
     assert e.value.code == 3
+    # the other handles of the library behave the same: no device, no result
+    Z = np.zeros((10, 5))
+    Z[4] = 0.1
+    traj = pb.NamedTrajectory(Z, {"ψ̃": range(0, 4), "Δt": range(4, 5), "t": range(5, 6), "u": range(6, 7),
+                                  "du": range(7, 8), "ddu": range(8, 9)})
+    with pytest.raises(pb.PB2Error) as e:
+        pb.B200KnotLinearConstraints(traj)
+    assert e.value.code == 3
+    J = pb.KetInfidelityObjective(np.array([0, 1], complex), "ψ̃", traj) + pb.QuadraticRegularizer("u", traj, 1e-2)
+    with pytest.raises(pb.PB2Error) as e:
+        J.value(Z)                       # the handle is built on first use
+    assert e.value.code == 3
 
 
 def test_product_never_imports_oracle():
