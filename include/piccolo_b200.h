@@ -231,7 +231,9 @@ typedef struct pb2_obj_desc {
 typedef struct pb2_obj pb2_obj;
 int pb2_obj_create(const pb2_obj_desc* desc, pb2_obj** out);   /* copies everything it needs */
 void pb2_obj_destroy(pb2_obj* h);
-/* J -> *J; gradient (K*D doubles) -> grad unless NULL.  space = PB2_HOST or PB2_DEVICE for Z, J, grad */
+/* J -> *J; gradient (K*D doubles) -> grad unless NULL.  space = PB2_HOST or PB2_DEVICE for Z, J, grad.
+ * J is summed in knot order (bitwise reproducible).  A handle owns per-launch scratch: calls on one
+ * handle must be ordered on one stream (use one handle per stream for concurrent evaluations). */
 int pb2_obj_value_gradient(pb2_obj* h, const double* Z, double* J, double* grad, int space);
 int pb2_obj_value_gradient_async(pb2_obj* h, const double* dZ, double* dJ, double* dgrad, void* stream);
 
