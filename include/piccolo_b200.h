@@ -145,6 +145,18 @@ int pb2_enable_peer_access(int32_t device, int32_t peer);
 void* pb2_stream(const pb2_handle* h);
 int pb2_sync(pb2_handle* h);
 
+/* Per-handle options (all default 0).
+ *  PB2_OPT_EARLY_Z  the caller promises that the trajectory buffer dZ passed to the *_async entry points is
+ *                   complete before the kernel enqueued immediately before the call on that stream STARTS
+ *                   (true whenever Z arrives by a copy -- the Ipopt callback case -- and for back-to-back
+ *                   evaluator calls on one trajectory).  The kernels are launched with programmatic stream
+ *                   serialization; with this promise they load Z, build G(u_k) and run the propagator tiles
+ *                   before `griddepcontrol.wait`, so consecutive callbacks overlap one launch's drain with the
+ *                   next one's prologue.  Outputs are never written before the wait.  The host-pointer entry
+ *                   points always have this property (the library itself copies Z on the handle's stream). */
+enum { PB2_OPT_EARLY_Z = 1 };
+int pb2_set_option(pb2_handle* h, int32_t option, int64_t value);
+
 /* ---- linear knot constraints evaluated in the same callbacks -----------------
  * DerivativeIntegrator(x, xdot, traj): r_k = x_{k+1} - x_k - dt_k xdot_k   (u -> du, du -> ddu;
  *   src/control/templates/smooth_pulse_problem.jl:267-275, spline_pulse_problem.jl:363-366)

@@ -11,6 +11,7 @@ PB2_HOST, PB2_DEVICE = 0, 1
 PB2_ALG_AUTO, PB2_ALG_GENERIC, PB2_ALG_DMMA = 0, 1, 2
 KIND = {"ket": PB2_KET, "unitary": PB2_UNITARY, "density": PB2_DENSITY}
 ALG = {"auto": PB2_ALG_AUTO, "generic": PB2_ALG_GENERIC, "dmma": PB2_ALG_DMMA}
+OPT = {"early_z": 1}
 
 # every symbol include/piccolo_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
@@ -24,7 +25,7 @@ SYMBOLS = [
     "pb2_aux_structure_jac", "pb2_aux_structure_hess", "pb2_aux_residual_jacobian", "pb2_aux_hess_lagrangian",
     "pb2_aux_residual_jacobian_async",
     "pb2_obj_create", "pb2_obj_destroy", "pb2_obj_value_gradient", "pb2_obj_value_gradient_async",
-    "pb2_stream", "pb2_sync", "pb2_host_alloc", "pb2_host_free", "pb2_launch_count",
+    "pb2_stream", "pb2_sync", "pb2_set_option", "pb2_host_alloc", "pb2_host_free", "pb2_launch_count",
 ]
 
 
@@ -128,6 +129,7 @@ def load_library():
     L.pb2_enable_peer_access.argtypes = [ctypes.c_int32, ctypes.c_int32]
     L.pb2_residual_jacobian_exchange_async.argtypes = [H, vp, ctypes.c_int32, ctypes.c_int32,
                                                        ctypes.POINTER(vp), ctypes.c_int64, vp]
+    L.pb2_set_option.argtypes = [H, ctypes.c_int32, ctypes.c_int64]
     L.pb2_stream.argtypes = [H]
     L.pb2_stream.restype = ctypes.c_void_p
     L.pb2_aux_create.argtypes = [ctypes.POINTER(pb2_aux_desc), ctypes.POINTER(H)]

@@ -182,24 +182,26 @@ __device__ __forceinline__ void horner_step(double (&t)[2 * NT], const double (&
   }
   double ck = 0.0;
   if (MODE != 2) ck = lds_f64<0>(ck_addr);
+  // every additive term goes into the accumulators BEFORE the products (see knot_u8.cuh, u8_mma_acc:
+  // an FP64 CUDA-core instruction after the DMMAs would queue behind the other warps' tensor work)
   double d[NT][2];
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) dmma884z(d[nt], t[0], A[0][nt]);
-#pragma unroll
-  for (int kt = 1; kt < KT; ++kt)
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) dmma884(d[nt], t[kt], A[kt][nt]);
-#pragma unroll
   for (int i = 0; i < KT; ++i) {
-    double v = d[i >> 1][i & 1];
-    if (MODE == 1) v = fma(ck, base[i], v);
-    if (MODE == 0 && ((diag >> i) & 1u)) v += ck;
+    double v = 0.0;
+    if (MODE == 1) v = ck * base[i];
+    if (MODE == 0 && ((diag >> i) & 1u)) v = ck;
     if (cpl) {
 #pragma unroll
       for (int ww = 0; ww < W; ++ww) v = fma(ev[i][ww], y[i][ww], v);
     }
-    t[i] = v;
+    d[i >> 1][i & 1] = v;
   }
+#pragma unroll
+  for (int kt = 0; kt < KT; ++kt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) dmma884(d[nt], t[kt], A[kt][nt]);
+#pragma unroll
+  for (int i = 0; i < KT; ++i) t[i] = d[i >> 1][i & 1];
   PB2_STEP_STAMP(2);
 }
 

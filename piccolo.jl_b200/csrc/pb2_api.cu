@@ -26,6 +26,8 @@
 #include "knot_u8h.cuh"
 #include "knot_aux.cuh"
 #include "knot_objective.cuh"
+#include "knot_u8s.cuh"
+#include "knot_u8p.cuh"
 #include "host_pool.h"
 
 namespace {
@@ -101,6 +103,8 @@ struct pb2_handle {
   double* dTables = nullptr;   // [gfrag | norms (even) | theta | 1/k!] contiguous, the u8 kernels' smem order
   long long* dTrace = nullptr;
   long long* dTrace2 = nullptr;
+  long long* dTrace3 = nullptr;   // debug build: [launch 64][block 148][warp 16][8] stamps of the single-round kernels
+  int trace_launch = 0;
   int n_sm = 148, gpc_default = 3, gpc_override = 0;
   bool u8_ok = false;
   bool u8h_ok = false;
@@ -108,6 +112,9 @@ struct pb2_handle {
   int pdl = 1;
   int stagger_g = 0;
   int direct_last = 1;
+  int u8s = 0;             // first single-round draft (whole-knot slots), kept for A/B measurements (PB2_U8S=1)
+  int u8p = 1;             // single-round kernel for <= 7 knots per SM (knot_u8p.cuh); PB2_U8P=0 disables it
+  int early_z = 0;         // PB2_OPT_EARLY_Z: device-pointer calls may read Z before the programmatic dependency wait
   pb2::EllEntry* dEll = nullptr;
   // staging for host-pointer calls
   double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
@@ -133,12 +140,74 @@ pb2::KnotParams make_params(const pb2_handle* h) {
 }
 
 int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, int compact = 0,
-                  int n_peers = 0, double* const* peers = nullptr, int self = 0) {
+                  int n_peers = 0, double* const* peers = nullptr, int self = 0, int z_stable = 0) {
   if (h->nk() <= 0) return PB2_OK;
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.delta = ddelta; p.jac = djac;
   const bool aligned16 = ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0);
-  if (h->alg == PB2_ALG_DMMA && h->u8_ok && djac && aligned16 && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
+  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p && !h->u8s && djac && aligned16 && (p.D % 2 == 0) && (p.x_off % 2 == 0) &&
+      (p.m == 3 || p.m == 4) && h->plan.W == 1 && n_peers == 0 && h->nk() <= (int64_t)pb2::kU8pSlots * h->n_sm) {
+    // at most seven knots per SM: every knot of an SM in flight at once, propagator tiles first (knot_u8p.cuh)
+    pb2::U8pParams q{};
+    q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
+    q.nnz_jac = p.nnz_jac; q.max_sub = 4096; q.nk = (int)h->nk();
+    q.zlen = p.D + p.x_off + 128;
+    q.early_z = (z_stable || h->early_z) ? 1 : 0;
+    q.compact = compact; q.cstride = (p.m + 3) * 128;
+    q.tables = h->dTables; q.ell = h->dEll;
+    q.Z = dZ; q.delta = ddelta; q.jac = djac;
+#ifdef PB2_TRACE
+    q.trace = h->dTrace3; q.trace_id = (h->trace_launch++) % 64;
+#endif
+    const size_t smem = pb2::u8p_layout(q);
+    if (smem > kSmemLimit) return fail(PB2_EINVAL, "u8p resjac: knot column too large for the shared-memory staging");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)std::min<int64_t>(h->n_sm, q.nk));
+    cfg.blockDim = dim3(pb2::kU8pThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, pb2::u8p_kernel(h->plan.W), q);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("u8p resjac launch: ") + cudaGetErrorString(e));
+    h->launches++;
+    return PB2_OK;
+  }
+  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8s && djac && aligned16 && (p.D % 2 == 0) && (p.x_off % 2 == 0) &&
+      (p.m == 3 || p.m == 4) && !compact && n_peers == 0 &&
+      h->nk() <= (int64_t)pb2::kU8sSlots * h->n_sm) {
+    // at most seven knots per SM: single-round kernel, every knot of an SM in flight (EXPERIMENTAL, PB2_U8S=1)
+    pb2::U8sParams q{};
+    q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
+    q.nnz_jac = p.nnz_jac; q.max_sub = 4096; q.nk = (int)h->nk();
+    q.zlen = p.D + p.x_off + 128;
+    q.tables = h->dTables; q.ell = h->dEll;
+    q.Z = dZ; q.delta = ddelta; q.jac = djac;
+#ifdef PB2_TRACE
+    q.trace = h->dTrace3; q.trace_id = (h->trace_launch++) % 64;
+#endif
+    const size_t smem = pb2::u8s_layout(q);
+    if (smem > kSmemLimit) return fail(PB2_EINVAL, "u8s resjac: knot column too large for the shared-memory staging");
+    auto kern = pb2::u8s_kernel(h->plan.W);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)std::min<int64_t>(h->n_sm, q.nk));
+    cfg.blockDim = dim3(64 * pb2::kU8sSlots);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, q);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("u8s resjac launch: ") + cudaGetErrorString(e));
+  } else if (h->alg == PB2_ALG_DMMA && h->u8_ok && djac && aligned16 && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
     // the 3-qubit unitary shape: warp-specialised kernel (producer warp + (E,X) warp + jet warps)
     const pb2::DmmaPlan& pl = h->plan;
     pb2::U8Params q{};
@@ -436,10 +505,16 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     if (const char* env = std::getenv("PB2_PDL")) h->pdl = std::atoi(env);
     if (const char* env = std::getenv("PB2_STAGGER_G")) h->stagger_g = std::atoi(env);
     if (const char* env = std::getenv("PB2_DIRECT_LAST")) h->direct_last = std::atoi(env);
+    if (const char* env = std::getenv("PB2_U8S")) h->u8s = std::atoi(env);
+    if (const char* env = std::getenv("PB2_U8P")) h->u8p = std::atoi(env);
+    if (const char* env = std::getenv("PB2_EARLY_Z")) h->early_z = std::atoi(env);
     h->u8_ok = h->plan.iso && d.b == 16 && d.n_b == 8 && d.m >= 1 && d.m <= 6 && !std::getenv("PB2_NO_U8");
-    if (h->u8_ok)
+    if (h->u8_ok) {
       PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8_kernel(h->plan.W), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemLimit));
+      PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8p_kernel(h->plan.W), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kSmemLimit));
+    }
     // the tensor-core Hessian additionally uses E^T = exp(-dt G): every generator anti-symmetric
     // (true for the isomorphism of any Hermitian Hamiltonian, isomorphisms.jl:350,359)
     bool antisym = true;
@@ -463,6 +538,8 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
       PB2_CUDA_H(cudaMemcpyToSymbol(pb2::g_trace2, &t2, sizeof(t2)));
       h->dTrace2 = t2;
     }
+    PB2_CUDA_H(cudaMalloc(&h->dTrace3, (size_t)64 * 148 * 16 * 8 * sizeof(long long)));
+    PB2_CUDA_H(cudaMemset(h->dTrace3, 0, (size_t)64 * 148 * 16 * 8 * sizeof(long long)));
 #endif
   }
 #undef PB2_CUDA_H
@@ -487,6 +564,7 @@ void pb2_destroy(pb2_handle* h) {
     if (e) cudaEventDestroy(e);
   if (h->dTrace) cudaFree(h->dTrace);
   if (h->dTrace2) cudaFree(h->dTrace2);
+  if (h->dTrace3) cudaFree(h->dTrace3);
   for (double* p : {h->hZ, h->hDelta, h->hJac, h->hMu, h->hHess})
     if (p) cudaFreeHost(p);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -504,6 +582,15 @@ extern "C" int pb2_debug_trace(pb2_handle* h, long long* out) {   // 8 knots x 1
   if (!h || !h->dTrace) return PB2_EINVAL;
   cudaDeviceSynchronize();
   return cudaMemcpy(out, h->dTrace, 8 * 16 * 8 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : PB2_ECUDA;
+}
+extern "C" int pb2_debug_trace3(pb2_handle* h, long long* out) {   // 64 launches x 148 blocks x 16 warps x 8 stamps
+  if (!h || !h->dTrace3) return PB2_EINVAL;
+  cudaDeviceSynchronize();
+  const size_t n = (size_t)64 * 148 * 16 * 8 * sizeof(long long);
+  if (cudaMemcpy(out, h->dTrace3, n, cudaMemcpyDeviceToHost) != cudaSuccess) return PB2_ECUDA;
+  cudaMemset(h->dTrace3, 0, n);
+  h->trace_launch = 0;
+  return 0;
 }
 extern "C" int pb2_debug_trace2(pb2_handle* h, long long* out) {   // 16 warps x 20 steps x 4 stamps (last knot)
   if (!h || !h->dTrace2) return PB2_EINVAL;
@@ -641,6 +728,14 @@ int pb2_expand_compact_async(pb2_handle* h, const double* dcompact, int64_t n_kn
 
 void* pb2_stream(const pb2_handle* h) { return h ? (void*)h->stream : nullptr; }
 
+int pb2_set_option(pb2_handle* h, int32_t option, int64_t value) {
+  if (check(h)) return PB2_EINVAL;
+  switch (option) {
+    case PB2_OPT_EARLY_Z: h->early_z = value != 0; return PB2_OK;
+    default: return fail(PB2_EINVAL, "pb2_set_option: unknown option");
+  }
+}
+
 int pb2_sync(pb2_handle* h) {
   if (check(h)) return PB2_EINVAL;
   PB2_CUDA(cudaSetDevice(h->d.device));
@@ -678,7 +773,7 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
     if ((rc = ensure(&h->dZ, &h->hZ, nZ))) return rc;
     if ((rc = ensure(&h->dComp, &h->hComp, (size_t)(nk * cs)))) return rc;
     if ((rc = stage_in(h, Z, h->hZ, h->dZ, nZ))) return rc;
-    if ((rc = launch_resjac(h, h->dZ, nullptr, h->dComp, h->stream, 1))) return rc;
+    if ((rc = launch_resjac(h, h->dZ, nullptr, h->dComp, h->stream, 1, 0, nullptr, 0, 1))) return rc;
     const int nch_env = std::getenv("PB2_D2H_CHUNKS") ? std::atoi(std::getenv("PB2_D2H_CHUNKS")) : 8;
     const int nch = (int)std::min<int64_t>(std::min(16, std::max(1, nch_env)), std::max<int64_t>(1, nk / 32));
     const int64_t per = (nk + nch - 1) / nch;
@@ -733,7 +828,7 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
   if (delta && (rc = ensure(&h->dDelta, &h->hDelta, nD))) return rc;
   if (vals && (rc = ensure(&h->dJac, &h->hJac, nJ))) return rc;
   if ((rc = stage_in(h, Z, h->hZ, h->dZ, nZ))) return rc;
-  if ((rc = launch_resjac(h, h->dZ, delta ? h->dDelta : nullptr, vals ? h->dJac : nullptr, h->stream)))
+  if ((rc = launch_resjac(h, h->dZ, delta ? h->dDelta : nullptr, vals ? h->dJac : nullptr, h->stream, 0, 0, nullptr, 0, 1)))
     return rc;
   PendingOut po1{}, po2{};
   if (delta && (rc = stage_out_begin(h, delta, h->hDelta, h->dDelta, nD, po1))) return rc;

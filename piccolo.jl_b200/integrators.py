@@ -301,6 +301,10 @@ class B200BilinearIntegrator:
     def sync(self):
         capi.check(self._lib.pb2_sync(self._h))
 
+    def set_option(self, name, value):
+        """pb2_set_option (include/piccolo_b200.h): e.g. ``set_option("early_z", 1)``."""
+        capi.check(self._lib.pb2_set_option(self._h, capi.OPT[name], int(value)))
+
     @property
     def launch_count(self):
         return int(self._lib.pb2_launch_count(self._h))

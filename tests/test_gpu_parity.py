@@ -27,7 +27,20 @@ def make(p, algorithm="auto", **kw):
 
 
 def algorithms(p):
-    return ["generic"] if p.kind == "density" else ["generic", "auto"]
+    """Every kind is checked through both the jet kernels and whatever `auto` ships (for b <= 16 with sparse
+    drive generators -- C4's compact Lindbladian included -- that is the tensor-core kernel)."""
+    return ["generic", "auto"]
+
+
+def expected_auto(p):
+    """What PB2_ALG_AUTO must select (decided at construction, pb2_api.cu): the tensor-core path for
+    b <= 16 with at most 4 nonzeros per drive-generator row and at most 8 column tiles."""
+    if p.b > 16 or p.n_b > 8:
+        return "generic"
+    w = max([int((np.asarray(g) != 0).sum(1).max()) for g in p.Gj] + [0])
+    ncT = p.b // 2 if p.kind != "density" else p.b
+    tiles = (ncT + (1 + p.m) * p.n_b + 7) // 8
+    return "dmma" if (w <= 4 and tiles <= 8) else "generic"
 
 
 def check_all(p, Z, mu, B, hess=True):
@@ -51,6 +64,10 @@ def test_synthetic_configs_vs_oracle(cfg, K):
     p, Z, mu = C.trajectory(cfg, K)
     for alg in algorithms(p):
         B = make(p, alg)
+        if alg == "auto":
+            assert B.algorithm == expected_auto(p)
+            if cfg in (1, 2, 3, 4):
+                assert B.algorithm == "dmma"          # every BASELINE config ships on the tensor-core path
         check_all(p, Z, mu, B)
         B.close()
 
@@ -62,6 +79,8 @@ def test_golden_trajectories(name):
     mu = np.random.default_rng(1).standard_normal(p.dim)
     for alg in algorithms(p):
         B = make(p, alg)
+        if alg == "auto":
+            assert B.algorithm == expected_auto(p)
         check_all(p, Z, mu, B)
         if name in GU.TIGHT:
             d = np.empty(B.dim)
@@ -156,6 +175,70 @@ def test_full_size_properties_c3():
     d0, _ = B.residual_jacobian(Z0)
     assert np.abs(d0).max() < 1e-13
     # (7) Hessian: symmetric contraction check  z^T H z  vs second difference of mu.delta along z
+    h = B.hessian_values(Z, mu)
+    assert np.abs(h - CP.hessian_values(p, Z, mu)).max() < HESS_RTOL * np.abs(h).max()
+    B.close()
+
+
+def _strided_scipy_check(p, Z, d, v, stride, res_tol=RES_TOL, jac_tol=JAC_TOL):
+    for k in range(0, p.K - 1, stride):
+        pk = KN.make_problem(p.kind, p.G0, p.Gj, 2)
+        Zk = np.asfortranarray(Z[:, k:k + 2])
+        assert np.abs(d[k * p.n_x:(k + 1) * p.n_x] - KN.residual(pk, Zk)).max() < res_tol
+        assert np.abs(v[k * p.nnz_jac_knot:(k + 1) * p.nnz_jac_knot] - KN.jacobian_values(pk, Zk)).max() < jac_tol
+
+
+def test_full_size_c4_density_through_the_shipped_path():
+    """BASELINE config C4 as written (CatSystem Lindbladian, d = 4 -> compact iso 16, m = 2, K = 500) through
+    PB2_ALG_AUTO, which must select the tensor-core kernel (knot_dmma<2, W>): the non-normal compact
+    generator (integrators.jl:82-95, open_quantum_systems.jl:541-562, 607-636) is the risky case for a
+    norm-bounded Taylor action, so it is checked against BOTH oracles on every knot."""
+    p, Z, mu = C.trajectory(4, 500)
+    B = make(p, "auto")
+    assert B.algorithm == "dmma"
+    d, v = B.residual_jacobian(Z)
+    assert np.abs(d - CP.residual(p, Z)).max() < RES_TOL
+    assert np.abs(v - CP.jacobian_values(p, Z)).max() < JAC_TOL
+    assert np.abs(d - KN.residual(p, Z)).max() < RES_TOL            # SciPy Pade-13 + expm_frechet, all 499 knots
+    assert np.abs(v - KN.jacobian_values(p, Z)).max() < JAC_TOL
+    d1 = np.empty(B.dim)
+    B.evaluate_(d1, Z)                                               # residual-only launch (no jets)
+    assert np.abs(d1 - d).max() < PATH_TOL
+    h, ho = B.hessian_values(Z, mu), KN.hessian_values(p, Z, mu)
+    assert np.abs(h - ho).max() < HESS_RTOL * max(1.0, np.abs(ho).max())
+    # the jet kernels on the same inputs: two CUDA paths, one answer
+    Bg = make(p, "generic")
+    dg, vg = Bg.residual_jacobian(Z)
+    assert np.abs(dg - d).max() < PATH_TOL and np.abs(vg - v).max() < 1e-12
+    Bg.close()
+    # trace preservation of the Lindblad propagator: sum of the diagonal entries of rho is conserved,
+    # i.e. the rows of E that the compact iso assigns to Re rho_jj sum to the same functional
+    dd = int(round(np.sqrt(p.b)))
+    diag_rows = [j * (j + 1) // 2 + j for j in range(dd)]           # Re rho[j, j] in the compact order (isomorphisms.jl:181-189)
+    E = -v.reshape(p.K - 1, p.nnz_jac_knot)[:, :p.b * p.b].reshape(-1, p.b, p.b).transpose(0, 2, 1)   # E[k][row][col]
+    tr_row = E[:, diag_rows, :].sum(1)
+    want = np.zeros(p.b)
+    want[diag_rows] = 1.0
+    assert np.abs(tr_row - want).max() < 1e-13
+    B.close()
+
+
+def test_full_size_c5_eight_thousand_knots():
+    """BASELINE config C5 (the C3 system with K = 8000): the persistent kernels walk ~ 54 knots per SM,
+    several slab-ring wrap-arounds and both mbarrier phases.  Full C++-port parity, SciPy on a stride."""
+    p, Z, mu = C.trajectory(5, 8000)
+    B = make(p)
+    assert B.algorithm == "dmma"
+    d, v = B.residual_jacobian(Z)
+    assert np.abs(d - CP.residual(p, Z)).max() < RES_TOL
+    assert np.abs(v - CP.jacobian_values(p, Z)).max() < JAC_TOL
+    _strided_scipy_check(p, Z, d, v, 397)
+    V = v.reshape(p.K - 1, p.nnz_jac_knot)
+    E = -V[:, :p.b * p.b].reshape(-1, p.b, p.b)
+    assert np.abs(np.einsum("kij,kil->kjl", E, E) - np.eye(p.b)).max() < 1e-13
+    for c in range(1, p.n_b):
+        assert np.array_equal(V[:, :p.b * p.b], V[:, c * p.b * p.b:(c + 1) * p.b * p.b])
+    assert np.all(V[:, -p.n_x:] == 1.0)
     h = B.hessian_values(Z, mu)
     assert np.abs(h - CP.hessian_values(p, Z, mu)).max() < HESS_RTOL * np.abs(h).max()
     B.close()
@@ -355,6 +438,83 @@ def test_u8_kernel_substeps_nan_and_many_knots():
     assert np.array_equal(D2[ok], D[ok])
     assert np.array_equal(v2.reshape(p.K - 1, -1)[ok], V[ok])
     B.close()
+
+
+def _device_resjac(B, Z, early_z=False):
+    """The canonical (non-compact) device-pointer call, as the benchmark issues it."""
+    import torch
+    if early_z:
+        B.set_option("early_z", 1)
+    dZ = torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda()
+    dd = torch.full((B.dim,), np.nan, dtype=torch.float64, device="cuda")
+    dv = torch.full((B.nnz_jac,), np.nan, dtype=torch.float64, device="cuda")
+    B.residual_jacobian_device(dZ, dd, dv, None)
+    torch.cuda.synchronize()
+    return dd.cpu().numpy(), dv.cpu().numpy()
+
+
+@pytest.mark.parametrize("K", [1000, 2, 149, 700, 1037])
+def test_single_round_kernel_every_occupancy(K, monkeypatch):
+    """knot_u8p (all knots of an SM in flight, propagator tiles first) takes every 3-qubit call with at most
+    seven knots per SM: one knot in the whole grid, one per SM, ragged slot counts, the BASELINE size and the
+    largest eligible size.  Canonical arrays through device pointers, with and without the early-Z promise,
+    and compact records through the host-pointer path; the two-round kernel (PB2_U8P=0) must agree to
+    rounding, the C++ port to the parity tolerances."""
+    p, Z, mu = C.trajectory(3, K)
+    B = make(p, "dmma")
+    d, v = _device_resjac(B, Z)
+    assert not np.isnan(d).any() and not np.isnan(v).any()          # every entry written
+    assert np.abs(d - CP.residual(p, Z)).max() < RES_TOL
+    assert np.abs(v - CP.jacobian_values(p, Z)).max() < JAC_TOL
+    d_e, v_e = _device_resjac(B, Z, early_z=True)
+    assert np.array_equal(d, d_e) and np.array_equal(v, v_e)
+    dh, vh = B.residual_jacobian(Z)                                 # compact records + host expansion
+    assert np.array_equal(d, dh) and np.array_equal(v, vh)
+    import torch
+    dZ = torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda()
+    dv2 = torch.full((B.nnz_jac,), np.nan, dtype=torch.float64, device="cuda")
+    B.residual_jacobian_device(dZ, None, dv2, None)                  # Jacobian only (no delta output)
+    torch.cuda.synchronize()
+    assert np.array_equal(dv2.cpu().numpy(), v)
+    B.close()
+    monkeypatch.setenv("PB2_U8P", "0")
+    B2 = make(p, "dmma")
+    d2, v2 = _device_resjac(B2, Z)
+    assert np.abs(d2 - d).max() < PATH_TOL and np.abs(v2 - v).max() < PATH_TOL
+    B2.close()
+
+
+def test_single_round_kernel_substeps_nan_three_drives():
+    """Data-dependent Taylor sub-steps and NaN confinement in the single-round kernel; m = 3 leaves warp B
+    with one jet tile."""
+    p, Z, mu = C.trajectory(3, 700)
+    rng = np.random.default_rng(11)
+    big = rng.choice(p.K - 1, size=30, replace=False)
+    Z[p.dt_off, big] = np.geomspace(0.3, 12.0, big.size)
+    B = make(p, "dmma")
+    d, v = _device_resjac(B, Z, early_z=True)
+    ref_d, ref_v = CP.residual(p, Z), CP.jacobian_values(p, Z)
+    assert np.abs(d - ref_d).max() < 1e-10 and np.abs(v - ref_v).max() < 5e-9
+    small = np.setdiff1d(np.arange(p.K - 1), big)
+    D, Dr = d.reshape(p.K - 1, -1), ref_d.reshape(p.K - 1, -1)
+    V, Vr = v.reshape(p.K - 1, -1), ref_v.reshape(p.K - 1, -1)
+    assert np.abs(D[small] - Dr[small]).max() < RES_TOL and np.abs(V[small] - Vr[small]).max() < JAC_TOL
+    Z2 = Z.copy(order="F")
+    Z2[p.u_off + 1, 5] = np.nan
+    Z2[p.dt_off, 500] = np.inf
+    d2, v2 = _device_resjac(B, Z2)
+    D2 = d2.reshape(p.K - 1, -1)
+    assert np.isnan(D2[5]).all() and np.isnan(D2[500]).all()
+    ok = np.setdiff1d(np.arange(p.K - 1), [5, 500])
+    assert np.array_equal(D2[ok], D[ok]) and np.array_equal(v2.reshape(p.K - 1, -1)[ok], V[ok])
+    B.close()
+    p3 = KN.make_problem("unitary", p.G0, list(p.Gj[:3]), 400)      # three of C3's drives: ELL width stays 1
+    Z3 = np.asfortranarray(rng.standard_normal((p3.D, 400)) * 0.3)
+    Z3[p3.dt_off, :] = 0.05 + 0.1 * rng.random(400)
+    B3 = make(p3, "dmma")
+    d3, v3 = _device_resjac(B3, Z3)
+    assert np.abs(d3 - CP.residual(p3, Z3)).max() < 1e-11 and np.abs(v3 - CP.jacobian_values(p3, Z3)).max() < 1e-10
+    B3.close()
 
 
 def test_u8_kernel_is_deterministic_and_matches_general_kernel(monkeypatch):
