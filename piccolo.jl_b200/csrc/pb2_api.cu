@@ -114,6 +114,9 @@ struct pb2_handle {
   int direct_last = 1;
   int u8s = 0;             // first single-round draft (whole-knot slots), kept for A/B measurements (PB2_U8S=1)
   int u8p = 1;             // single-round kernel for <= 7 knots per SM (knot_u8p.cuh); PB2_U8P=0 disables it
+  double* dTablesP = nullptr;   // knot_u8p's table blob (u8p_tables)
+  bool u8p_ok = false, u8p_unit = false;
+  double u8p_cj[4] = {1.0, 1.0, 1.0, 1.0};
   int early_z = 0;         // PB2_OPT_EARLY_Z: device-pointer calls may read Z before the programmatic dependency wait
   pb2::EllEntry* dEll = nullptr;
   // staging for host-pointer calls
@@ -145,8 +148,8 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.delta = ddelta; p.jac = djac;
   const bool aligned16 = ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0);
-  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p && !h->u8s && djac && aligned16 && (p.D % 2 == 0) && (p.x_off % 2 == 0) &&
-      (p.m == 3 || p.m == 4) && h->plan.W == 1 && n_peers == 0 && h->nk() <= (int64_t)pb2::kU8pSlots * h->n_sm) {
+  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8p && !h->u8s && djac && aligned16 && (p.D % 2 == 0) &&
+      (p.x_off % 2 == 0) && n_peers == 0 && h->nk() <= (int64_t)pb2::kU8pSlots * h->n_sm) {
     // at most seven knots per SM: every knot of an SM in flight at once, propagator tiles first (knot_u8p.cuh)
     pb2::U8pParams q{};
     q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
@@ -154,7 +157,8 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.zlen = p.D + p.x_off + 128;
     q.early_z = (z_stable || h->early_z) ? 1 : 0;
     q.compact = compact; q.cstride = (p.m + 3) * 128;
-    q.tables = h->dTables; q.ell = h->dEll;
+    q.tables = h->dTablesP; q.ell = h->dEll;
+    for (int j = 0; j < 4; ++j) q.cj[j] = h->u8p_cj[j];
     q.Z = dZ; q.delta = ddelta; q.jac = djac;
 #ifdef PB2_TRACE
     q.trace = h->dTrace3; q.trace_id = (h->trace_launch++) % 64;
@@ -171,7 +175,7 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = h->pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, pb2::u8p_kernel(h->plan.W), q);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, pb2::u8p_kernel(h->u8p_unit), q);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("u8p resjac launch: ") + cudaGetErrorString(e));
     h->launches++;
@@ -512,8 +516,18 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     if (h->u8_ok) {
       PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8_kernel(h->plan.W), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kSmemLimit));
-      PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8p_kernel(h->plan.W), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kSmemLimit));
+      // the single-round kernel: m = 3 or 4 drives whose generators have one nonzero per row (ELL width 1)
+      std::vector<double> blob;
+      if ((d.m == 3 || d.m == 4) && pb2::u8p_tables(h->plan, d.m, blob, h->u8p_unit, h->u8p_cj)) {
+        double* tabp = blob.data() + blob.size() - 40;
+        for (int q = 0; q <= pb2::kMaxDeg; ++q) { tabp[q] = theta[q]; tabp[20 + q] = invfact[q]; }
+        if (std::getenv("PB2_NO_UNIT")) h->u8p_unit = false;
+        PB2_CUDA_H(cudaMalloc(&h->dTablesP, blob.size() * sizeof(double)));
+        PB2_CUDA_H(cudaMemcpy(h->dTablesP, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
+        PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8p_kernel(h->u8p_unit), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)kSmemLimit));
+        h->u8p_ok = true;
+      }
     }
     // the tensor-core Hessian additionally uses E^T = exp(-dt G): every generator anti-symmetric
     // (true for the isomorphism of any Hermitian Hamiltonian, isomorphisms.jl:350,359)
@@ -538,8 +552,8 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
       PB2_CUDA_H(cudaMemcpyToSymbol(pb2::g_trace2, &t2, sizeof(t2)));
       h->dTrace2 = t2;
     }
-    PB2_CUDA_H(cudaMalloc(&h->dTrace3, (size_t)64 * 148 * 16 * 8 * sizeof(long long)));
-    PB2_CUDA_H(cudaMemset(h->dTrace3, 0, (size_t)64 * 148 * 16 * 8 * sizeof(long long)));
+    PB2_CUDA_H(cudaMalloc(&h->dTrace3, (size_t)64 * 148 * 16 * 40 * sizeof(long long)));
+    PB2_CUDA_H(cudaMemset(h->dTrace3, 0, (size_t)64 * 148 * 16 * 40 * sizeof(long long)));
 #endif
   }
 #undef PB2_CUDA_H
@@ -558,6 +572,7 @@ void pb2_destroy(pb2_handle* h) {
   if (h->dNorms) cudaFree(h->dNorms);
   if (h->dTab) cudaFree(h->dTab);
   if (h->dTables) cudaFree(h->dTables);
+  if (h->dTablesP) cudaFree(h->dTablesP);
   if (h->dComp) cudaFree(h->dComp);
   if (h->hComp) cudaFreeHost(h->hComp);
   for (cudaEvent_t e : h->chunk_ev)
@@ -586,7 +601,7 @@ extern "C" int pb2_debug_trace(pb2_handle* h, long long* out) {   // 8 knots x 1
 extern "C" int pb2_debug_trace3(pb2_handle* h, long long* out) {   // 64 launches x 148 blocks x 16 warps x 8 stamps
   if (!h || !h->dTrace3) return PB2_EINVAL;
   cudaDeviceSynchronize();
-  const size_t n = (size_t)64 * 148 * 16 * 8 * sizeof(long long);
+  const size_t n = (size_t)64 * 148 * 16 * 40 * sizeof(long long);
   if (cudaMemcpy(out, h->dTrace3, n, cudaMemcpyDeviceToHost) != cudaSuccess) return PB2_ECUDA;
   cudaMemset(h->dTrace3, 0, n);
   h->trace_launch = 0;

@@ -517,6 +517,32 @@ def test_single_round_kernel_substeps_nan_three_drives():
     B3.close()
 
 
+def test_single_round_kernel_general_drive_magnitudes(monkeypatch):
+    """Drive generators whose nonzeros differ in magnitude take the multiply form of the coupling term
+    (template UNIT = false); forcing that form on C3 (PB2_NO_UNIT) must reproduce the sign-flip form."""
+    p, Z, mu = C.trajectory(3, 500)
+    B = make(p, "dmma")
+    d, v = _device_resjac(B, Z)
+    B.close()
+    monkeypatch.setenv("PB2_NO_UNIT", "1")
+    B = make(p, "dmma")
+    d2, v2 = _device_resjac(B, Z)
+    B.close()
+    monkeypatch.delenv("PB2_NO_UNIT")
+    assert np.abs(d2 - d).max() < PATH_TOL and np.abs(v2 - v).max() < PATH_TOL
+    # H_j -> D H_j D with a positive diagonal D: still Hermitian, still one nonzero per row, magnitudes differ
+    dd = np.linspace(0.6, 1.7, 8)
+    P = np.diag(np.concatenate([dd, dd]))
+    Gj = [P @ g @ P for g in p.Gj]
+    pn = KN.make_problem("unitary", p.G0, Gj, 300)
+    Zn = np.asfortranarray(Z[:, :300])
+    Bn = make(pn, "dmma")
+    dn, vn = _device_resjac(Bn, Zn)
+    assert np.abs(dn - CP.residual(pn, Zn)).max() < RES_TOL and np.abs(vn - CP.jacobian_values(pn, Zn)).max() < JAC_TOL
+    assert np.abs(dn - KN.residual(pn, Zn)).max() < RES_TOL and np.abs(vn - KN.jacobian_values(pn, Zn)).max() < JAC_TOL
+    Bn.close()
+
+
 def test_u8_kernel_is_deterministic_and_matches_general_kernel(monkeypatch):
     """Same inputs -> bit-identical outputs across launches; the general tensor-core kernel (forced
     through PB2_NO_U8) agrees to rounding."""

@@ -27,7 +27,7 @@ for i in range(3):
 torch.cuda.synchronize()
 lib = pb.load_library()
 lib.pb2_debug_trace3.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
-out = np.zeros(64 * 148 * 16 * 8, dtype=np.int64)
+out = np.zeros(64 * 148 * 16 * 40, dtype=np.int64)
 assert lib.pb2_debug_trace3(B._h, out.ctypes.data) == 0      # also resets the launch counter
 g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g, stream=st):
@@ -40,7 +40,8 @@ g.replay()
 torch.cuda.synchronize()
 # the captured launches carry trace ids 0..NL-1 (ids are baked at capture time)
 assert lib.pb2_debug_trace3(B._h, out.ctypes.data) == 0
-T = out.reshape(64, 148, 16, 8)[:NL]
+T = out[:64 * 148 * 16 * 8].reshape(64, 148, 16, 8)[:NL]
+S = out[64 * 148 * 16 * 8:].reshape(64, 148, 16, 32)[:NL]
 U8P = os.environ.get("PB2_U8S", "0") != "1"      # default: the shipped single-round kernel (knot_u8p)
 if U8P:
     names = ["entry", "armed", "landed", "prepared", "E_done", "horner_end", "slab_issue", "end"]
@@ -78,3 +79,13 @@ for b in (0, 1, 50, 110, 111, 147):
             rows.append(f"w{w:2d}: " + " ".join(f"{n}={int(t[i] - base) if t[i] > 0 else -1:6d}" for i, n in enumerate(names)))
     print(f"launch {l} block {b} smid {int(smid[l, b])} duration {int(dur[l, b])}")
     print("\n".join(rows))
+
+if U8P:
+    print("per-step stamps (start of step, after the exchange barrier), cycles since CTA entry; launch", l)
+    for b in (0, 50):
+        for w in range(16):
+            st = S[l, b, w]
+            if st.max() > 0:
+                base = ent[l, b]
+                print(f"block {b} w{w:2d}: " + " ".join(f"{int(v - base) if v > 0 else -1}" for v in st[:24]) +
+                      f" | prep " + " ".join(f"{int(v - base) if v > 0 else -1}" for v in st[24:32]))
