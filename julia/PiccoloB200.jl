@@ -1,7 +1,8 @@
 # PiccoloB200.jl -- thin `ccall` shim that plugs libpiccolo_b200.so (include/piccolo_b200.h) into
 # Piccolo.jl's existing integrator extension point.
 #
-# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia toolchain and DirectTrajOpt.jl
+# NOT EXECUTED IN THIS REPOSITORY'S CI (field and helper names below were checked against the reference
+# source by reading it, e.g. QuantumSystem.H_drives / drive_matrix / compact_lindbladian_generators): the build image has no Julia toolchain and DirectTrajOpt.jl
 # is not vendored in the reference, so the exact abstract-method signatures below are the ones
 # visible from the reference's call sites:
 #   evaluate!(δ, B, traj)                    src/control/integrators.jl:311, display/inspect.jl:623
@@ -65,15 +66,29 @@ mutable struct B200BilinearIntegrator <: AbstractIntegrator
 end
 
 # ---- generator factors: exactly what the reference's closures add up per knot --------------------
-# G(u) = G_drift + Σ_j u_j G_drives[j]                   src/quantum/systems/quantum_systems.jl:212-227
-generator_parts(sys::QuantumSystem) = (Matrix(sys.G_drift), [Matrix(G) for G in sys.G_drives])
-# compact Lindbladian factors P·(G(ad_vec H) [+ Σ iso_D(L)])·L   open_quantum_systems.jl:541-562
+# G(u) = G(H_drift) + Σ_j u_j G(H_j).  The systems store the Hamiltonian terms (H_drift, H_drives::Vector of
+# AbstractDrive: src/quantum/systems/quantum_systems.jl:60-71, open_quantum_systems.jl:30-41), not generator
+# matrices; the isomorphism is Isomorphisms.G (src/quantum/primitives/isomorphisms.jl:350,359) as in the
+# closure built at quantum_systems.jl:212-227.
+generator_parts(sys::QuantumSystem) = (
+    Matrix{Float64}(Piccolo.Isomorphisms.G(sys.H_drift)),
+    [Matrix{Float64}(Piccolo.Isomorphisms.G(Piccolo.drive_matrix(d))) for d in sys.H_drives],
+)
+# Compact Lindbladian: the reference's integrator (integrators.jl:82-95) adds Σ_j rate_j 𝒢c_dissipators[j] to
+# the Hamiltonian drift through compact_generator_closure (open_quantum_systems.jl:607-636).  For
+# LinearDissipators the rate is a constant, so it folds into the drift factor exactly;
+# compact_lindbladian_generators (open_quantum_systems.jl:576-590) is the reference's own helper that does it.
 function generator_parts(sys::OpenQuantumSystem)
-    𝒢d, 𝒢s, _ = Piccolo.compact_lindbladian_parts(sys)
-    return Matrix(𝒢d), [Matrix(G) for G in 𝒢s]
+    𝒢d, 𝒢s = Piccolo.compact_lindbladian_generators(sys)
+    return Matrix{Float64}(𝒢d), [Matrix{Float64}(G) for G in 𝒢s]
 end
 
-linear_drives_only(sys) = all(d -> d isa Piccolo.LinearDrive, sys.drives)   # drives.jl:93-99
+# what the C ABI can express: coefficients u[index] (LinearDrive, drives.jl:52-55) and constant dissipation
+# rates (LinearDissipator, dissipators.jl:33-39); anything else keeps the reference's integrator
+linear_drives_only(sys) = all(d -> d isa Piccolo.LinearDrive, sys.H_drives)
+linear_drives_only(sys::OpenQuantumSystem) =
+    all(d -> d isa Piccolo.LinearDrive, sys.H_drives) &&
+    !Piccolo.has_nonlinear_dissipators(getfield(sys, :dissipators))
 
 # ---- constructors mirroring src/control/integrators.jl:35-95 ---------------------------------------
 # Anything the C ABI cannot express (nonlinear / time-dependent drives) falls through to the

@@ -120,7 +120,8 @@ __device__ __forceinline__ void u8p_step_A(double (&tX)[4], double (&tJ)[2][4], 
                                            const double (&bJ)[2][4], const double (&A)[4][2], uint32_t ypub,
                                            uint32_t ck_addr, uint32_t ck_next_addr, int bar, double (&accX)[4],
                                            const double (&ev)[2][4], const int (&sg)[2][4], const uint32_t (&yad)[2][4],
-                                           bool mma, double* dT_out, U8pStepTrace& st) {
+                                           bool mma, double* dT_out, U8pStepTrace& st, bool depwait = true,
+                                           uint32_t a_graw = 0) {
   U8P_STEP_STAMP(st.base, st.n); ++st.n;
 #pragma unroll
   for (int i = 0; i < 4; ++i) sts_f64<0>(ypub + i * 256, tX[i]);
@@ -144,8 +145,17 @@ __device__ __forceinline__ void u8p_step_A(double (&tX)[4], double (&tJ)[2][4], 
   if (dT_out) {
     // the knot's final step: every earlier grid of the stream has long completed (the wait returns at once)
     double dT[2][2];
-    u8_mma(dT, tX, A);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (a_graw) {
+      // the caller iterates on a scaled generator (knot_u8q: dt G): this one product takes the unscaled
+      // fragments, kept in shared memory for it
+      double Gr[4][2];
+#pragma unroll
+      for (int s8 = 0; s8 < 8; ++s8) Gr[s8 >> 1][s8 & 1] = lds_f64<0>(a_graw + 256u * (uint32_t)s8);
+      u8_mma(dT, tX, Gr);
+    } else {
+      u8_mma(dT, tX, A);
+    }
+    if (depwait) asm volatile("griddepcontrol.wait;" ::: "memory");
     stg_f64x2(dT_out, -dT[0][0], -dT[0][1]);
     stg_f64x2(dT_out + 8, -dT[1][0], -dT[1][1]);
   }

@@ -28,6 +28,7 @@
 #include "knot_objective.cuh"
 #include "knot_u8s.cuh"
 #include "knot_u8p.cuh"
+#include "knot_u8q.cuh"
 #include "host_pool.h"
 
 namespace {
@@ -38,6 +39,19 @@ int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+
+// Every entry point works on its handle's device and leaves the caller's current device as it found it
+// (a host framework -- torch, CUDA.jl -- driving several GPUs from one process relies on it).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 #define PB2_CUDA(call)                                                                   \
   do {                                                                                   \
@@ -114,7 +128,12 @@ struct pb2_handle {
   int direct_last = 1;
   int u8s = 0;             // first single-round draft (whole-knot slots), kept for A/B measurements (PB2_U8S=1)
   int u8p = 1;             // single-round kernel for <= 7 knots per SM (knot_u8p.cuh); PB2_U8P=0 disables it
+  int u8q = 1;             // small-CTA kernel (knot_u8q.cuh); PB2_U8Q=0 disables it, PB2_U8Q=2 takes every size
+  int u8q_ns = 2;          // knots per CTA: 4 (two CTAs per SM) or 2 (four CTAs per SM); PB2_U8Q_NS
+  int u8q_space = 0;       // minimum spacing (cycles) of the product phases of CTAs sharing an SM; PB2_U8Q_SPACE
+  unsigned long long* dSmClock = nullptr;
   double* dTablesP = nullptr;   // knot_u8p's table blob (u8p_tables)
+  double* dTablesQ = nullptr;   // knot_u8q's table blob (u8q_tables)
   bool u8p_ok = false, u8p_unit = false;
   double u8p_cj[4] = {1.0, 1.0, 1.0, 1.0};
   int early_z = 0;         // PB2_OPT_EARLY_Z: device-pointer calls may read Z before the programmatic dependency wait
@@ -148,6 +167,54 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.delta = ddelta; p.jac = djac;
   const bool aligned16 = ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0);
+  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8q && !h->u8s && djac && aligned16 && (p.D % 2 == 0) &&
+      (p.x_off % 2 == 0) && n_peers == 0 && (h->u8q >= 2 || h->nk() <= (int64_t)7 * h->n_sm)) {
+    // two 256-thread CTAs per SM, at most four knots each: one CTA's prologue and tail run underneath the
+    // other one's products, and a freed half-SM goes to the next grid of the stream at once (knot_u8q.cuh)
+    pb2::U8qParams q{};
+    q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
+    q.nnz_jac = p.nnz_jac; q.max_sub = 4096; q.nk = (int)h->nk();
+    q.zlen = p.D + p.x_off + 128;
+    q.early_z = (z_stable || h->early_z) ? 1 : 0;
+    q.compact = compact; q.cstride = (p.m + 3) * 128;
+    q.tables = h->dTablesQ; q.ell = h->dEll;
+    for (int j = 0; j < 4; ++j) q.cj[j] = h->u8p_cj[j];
+    q.Z = dZ; q.delta = ddelta; q.jac = djac;
+#ifdef PB2_TRACE
+    q.trace = h->dTrace3; q.trace_id = (h->trace_launch++) % 64;
+#endif
+    const int ns = h->u8q_ns, cps = 8 / ns;   // knots per CTA, CTAs per SM
+    q.space = h->u8q_space; q.sm_clock = h->dSmClock;
+    q.nowait = std::getenv("PB2_NOWAIT") ? std::atoi(std::getenv("PB2_NOWAIT")) : 0;   // EXPERIMENT
+    q.pro = std::getenv("PB2_U8Q_PRO") ? std::atoi(std::getenv("PB2_U8Q_PRO")) : 3000;
+    unsigned grid;
+    if (q.nk <= 7 * h->n_sm) {
+      // cps CTAs per SM; the last n_sm CTAs own one knot less: blocks b, b + n_sm, ... share an SM on an idle
+      // device (7 knots per SM, as evenly as 6.75 allows); under back-to-back launches the hardware balances
+      grid = (unsigned)std::min(cps * h->n_sm, q.nk);
+      q.split = (cps - 1) * h->n_sm;
+    } else {
+      grid = (unsigned)((q.nk + ns - 1) / ns);
+      q.split = 0;
+    }
+    const size_t smem = pb2::u8q_layout(q, ns);
+    if (smem > kSmemLimit / cps) return fail(PB2_EINVAL, "u8q resjac: knot column too large for the shared-memory staging");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(64 * ns);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, pb2::u8q_kernel(h->u8p_unit, ns), q);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("u8q resjac launch: ") + cudaGetErrorString(e));
+    h->launches++;
+    return PB2_OK;
+  }
   if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8p && !h->u8s && djac && aligned16 && (p.D % 2 == 0) &&
       (p.x_off % 2 == 0) && n_peers == 0 && h->nk() <= (int64_t)pb2::kU8pSlots * h->n_sm) {
     // at most seven knots per SM: every knot of an SM in flight at once, propagator tiles first (knot_u8p.cuh)
@@ -418,7 +485,7 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     return fail(PB2_ENODEVICE, "pb2_create: no CUDA device (this library has no CPU path)");
   }
   if (d.device < 0 || d.device >= ndev) return fail(PB2_EINVAL, "pb2_create: bad device ordinal");
-  PB2_CUDA(cudaSetDevice(d.device));
+  DeviceGuard guard_1(d.device);
 
   pb2_handle* h = new (std::nothrow) pb2_handle();
   if (!h) return fail(PB2_ENOMEM, "pb2_create: out of memory");
@@ -471,11 +538,12 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
   for (int q = 1; q <= pb2::kMaxDeg; ++q) theta[q] = theta_bound(q);
   PB2_CUDA_H(cudaMemcpyToSymbol(pb2::c_theta, theta, sizeof(theta)));
 
-  if (h->alg == PB2_ALG_GENERIC)
-    PB2_CUDA_H(cudaFuncSetAttribute(pb2::knot_generic_kernel<1, kNT>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cfg1.smem));
+  // the attribute belongs to the FUNCTION, not to this handle: always the device limit, so that a second live
+  // handle with a smaller generator can never lower the cap under an earlier handle's launches
+  PB2_CUDA_H(cudaFuncSetAttribute(pb2::knot_generic_kernel<1, kNT>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
   PB2_CUDA_H(cudaFuncSetAttribute(pb2::knot_generic_kernel<2, kNT>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->cfg2.smem));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
   if (h->alg == PB2_ALG_DMMA) {
     const size_t ng = h->plan.gfrag.size() * sizeof(double), ne = h->plan.ell.size() * sizeof(pb2::EllEntry);
     const size_t nn = h->plan.norms.size() * sizeof(double);
@@ -511,6 +579,9 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     if (const char* env = std::getenv("PB2_DIRECT_LAST")) h->direct_last = std::atoi(env);
     if (const char* env = std::getenv("PB2_U8S")) h->u8s = std::atoi(env);
     if (const char* env = std::getenv("PB2_U8P")) h->u8p = std::atoi(env);
+    if (const char* env = std::getenv("PB2_U8Q")) h->u8q = std::atoi(env);
+    if (const char* env = std::getenv("PB2_U8Q_NS")) h->u8q_ns = std::atoi(env) == 2 ? 2 : 4;
+    if (const char* env = std::getenv("PB2_U8Q_SPACE")) h->u8q_space = std::atoi(env);
     if (const char* env = std::getenv("PB2_EARLY_Z")) h->early_z = std::atoi(env);
     h->u8_ok = h->plan.iso && d.b == 16 && d.n_b == 8 && d.m >= 1 && d.m <= 6 && !std::getenv("PB2_NO_U8");
     if (h->u8_ok) {
@@ -526,6 +597,20 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
         PB2_CUDA_H(cudaMemcpy(h->dTablesP, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
         PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8p_kernel(h->u8p_unit), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)kSmemLimit));
+        for (int ns : {2, 4}) {
+          PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8q_kernel(h->u8p_unit, ns), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(kSmemLimit * ns / 8)));
+          PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8q_kernel(h->u8p_unit, ns), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        }
+        {
+          double tab40[40] = {0};
+          for (int q = 0; q <= pb2::kMaxDeg; ++q) { tab40[q] = theta[q]; tab40[20 + q] = invfact[q]; }
+          const std::vector<double> bq = pb2::u8q_tables(h->plan, d.m, tab40);
+          PB2_CUDA_H(cudaMalloc(&h->dTablesQ, bq.size() * sizeof(double)));
+          PB2_CUDA_H(cudaMemcpy(h->dTablesQ, bq.data(), bq.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+        PB2_CUDA_H(cudaMalloc(&h->dSmClock, 512 * sizeof(unsigned long long)));
+        PB2_CUDA_H(cudaMemset(h->dSmClock, 0, 512 * sizeof(unsigned long long)));
         h->u8p_ok = true;
       }
     }
@@ -563,7 +648,7 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
 
 void pb2_destroy(pb2_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->d.device);
+  DeviceGuard guard_d(h->d.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (double* p : {h->dG0, h->dGj, h->dZ, h->dDelta, h->dJac, h->dMu, h->dHess})
     if (p) cudaFree(p);
@@ -573,6 +658,8 @@ void pb2_destroy(pb2_handle* h) {
   if (h->dTab) cudaFree(h->dTab);
   if (h->dTables) cudaFree(h->dTables);
   if (h->dTablesP) cudaFree(h->dTablesP);
+  if (h->dTablesQ) cudaFree(h->dTablesQ);
+  if (h->dSmClock) cudaFree(h->dSmClock);
   if (h->dComp) cudaFree(h->dComp);
   if (h->hComp) cudaFreeHost(h->hComp);
   for (cudaEvent_t e : h->chunk_ev)
@@ -673,7 +760,7 @@ int pb2_residual_jacobian_async(pb2_handle* h, const double* dZ, double* ddelta,
                                 void* stream) {
   if (check(h)) return PB2_EINVAL;
   if (!dZ) return fail(PB2_EINVAL, "pb2_residual_jacobian_async: null Z");
-  PB2_CUDA(cudaSetDevice(h->d.device));
+  DeviceGuard guard_2(h->d.device);
   return launch_resjac(h, dZ, ddelta, dvals, (cudaStream_t)stream);
 }
 
@@ -681,7 +768,7 @@ int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu
                               void* stream) {
   if (check(h)) return PB2_EINVAL;
   if (!dZ || !dmu || !dvals) return fail(PB2_EINVAL, "pb2_hess_lagrangian_async: null argument");
-  PB2_CUDA(cudaSetDevice(h->d.device));
+  DeviceGuard guard_3(h->d.device);
   return launch_hess(h, dZ, dmu, dvals, (cudaStream_t)stream);
 }
 
@@ -694,7 +781,7 @@ int pb2_residual_jacobian_compact_async(pb2_handle* h, const double* dZ, double*
   if (check(h)) return PB2_EINVAL;
   if (!dZ || !dcompact) return fail(PB2_EINVAL, "pb2_residual_jacobian_compact_async: null argument");
   if (pb2_compact_stride(h) == 0) return fail(PB2_EINVAL, "pb2_residual_jacobian_compact_async: unsupported for this handle");
-  PB2_CUDA(cudaSetDevice(h->d.device));
+  DeviceGuard guard_4(h->d.device);
   return launch_resjac(h, dZ, nullptr, dcompact, (cudaStream_t)stream, 1);
 }
 
@@ -708,12 +795,12 @@ int pb2_residual_jacobian_exchange_async(pb2_handle* h, const double* dZ, int32_
   for (int r = 0; r < n_ranks; ++r)
     if (!gather_bufs[r] || ((uintptr_t)gather_bufs[r] % 16) != 0)
       return fail(PB2_EINVAL, "pb2_residual_jacobian_exchange_async: gather buffers must be 16-byte aligned device pointers");
-  PB2_CUDA(cudaSetDevice(h->d.device));
+  DeviceGuard guard_5(h->d.device);
   return launch_resjac(h, dZ, nullptr, gather_bufs[rank] + slot_offset, (cudaStream_t)stream, 1, n_ranks, gather_bufs, rank);
 }
 
 int pb2_enable_peer_access(int32_t device, int32_t peer) {
-  PB2_CUDA(cudaSetDevice(device));
+  DeviceGuard guard_6(device);
   int can = 0;
   PB2_CUDA(cudaDeviceCanAccessPeer(&can, device, peer));
   if (!can) return fail(PB2_EINVAL, "pb2_enable_peer_access: no peer access between these devices");
@@ -731,7 +818,7 @@ int pb2_expand_compact_async(pb2_handle* h, const double* dcompact, int64_t n_kn
   const int64_t cs = pb2_compact_stride(h);
   if (cs == 0) return fail(PB2_EINVAL, "pb2_expand_compact_async: unsupported for this handle");
   if (n_knots == 0) return PB2_OK;
-  PB2_CUDA(cudaSetDevice(h->d.device));
+  DeviceGuard guard_7(h->d.device);
   const int n_x = h->n_x();
   const int blocks = (int)std::min<int64_t>(n_knots, (int64_t)h->n_sm * 8);
   pb2::expand_compact_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dcompact, n_knots, (int)cs, (h->d.m + 1) * n_x,
@@ -753,7 +840,7 @@ int pb2_set_option(pb2_handle* h, int32_t option, int64_t value) {
 
 int pb2_sync(pb2_handle* h) {
   if (check(h)) return PB2_EINVAL;
-  PB2_CUDA(cudaSetDevice(h->d.device));
+  DeviceGuard guard_8(h->d.device);
   PB2_CUDA(cudaStreamSynchronize(h->stream));
   return PB2_OK;
 }
@@ -768,7 +855,7 @@ static int ensure(double** dev, double** host, size_t n) {
 int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double* vals, int space) {
   if (check(h)) return PB2_EINVAL;
   if (!Z) return fail(PB2_EINVAL, "pb2_residual_jacobian: null Z");
-  PB2_CUDA(cudaSetDevice(h->d.device));
+  DeviceGuard guard_9(h->d.device);
   if (space == PB2_DEVICE) {
     int rc = launch_resjac(h, Z, delta, vals, h->stream);
     if (rc) return rc;
@@ -867,7 +954,7 @@ int pb2_jacobian(pb2_handle* h, const double* Z, double* vals, int space) {
 int pb2_hess_lagrangian(pb2_handle* h, const double* Z, const double* mu, double* vals, int space) {
   if (check(h)) return PB2_EINVAL;
   if (!Z || !mu || !vals) return fail(PB2_EINVAL, "pb2_hess_lagrangian: null argument");
-  PB2_CUDA(cudaSetDevice(h->d.device));
+  DeviceGuard guard_10(h->d.device);
   if (space == PB2_DEVICE) {
     int rc = launch_hess(h, Z, mu, vals, h->stream);
     if (rc) return rc;
@@ -930,7 +1017,7 @@ int pb2_aux_create(const pb2_aux_desc* desc, pb2_aux** out) {
     return fail(PB2_ENODEVICE, "pb2_aux_create: no CUDA device (this library has no CPU path)");
   }
   if (d.device < 0 || d.device >= ndev) return fail(PB2_EINVAL, "pb2_aux_create: bad device ordinal");
-  PB2_CUDA(cudaSetDevice(d.device));
+  DeviceGuard guard_11(d.device);
   pb2_aux* h = new (std::nothrow) pb2_aux();
   if (!h) return fail(PB2_ENOMEM, "pb2_aux_create: out of memory");
   h->d = d;
@@ -957,7 +1044,7 @@ int pb2_aux_create(const pb2_aux_desc* desc, pb2_aux** out) {
 
 void pb2_aux_destroy(pb2_aux* h) {
   if (!h) return;
-  cudaSetDevice(h->d.device);
+  DeviceGuard guard_d(h->d.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (double* q : {h->dZ, h->dDelta, h->dJac, h->dMu, h->dHess})
     if (q) cudaFree(q);
@@ -1022,7 +1109,7 @@ static int aux_launch(pb2_aux* h, const double* dZ, const double* dmu, double* d
 
 int pb2_aux_residual_jacobian_async(pb2_aux* h, const double* dZ, double* ddelta, double* dvals, void* stream) {
   if (!h || !dZ) return fail(PB2_EINVAL, "pb2_aux_residual_jacobian_async: null argument");
-  PB2_CUDA(cudaSetDevice(h->d.device));
+  DeviceGuard guard_12(h->d.device);
   return aux_launch(h, dZ, nullptr, ddelta, dvals, nullptr, (cudaStream_t)stream);
 }
 
@@ -1033,7 +1120,7 @@ static int aux_ensure(double** dev, size_t n) {
 
 int pb2_aux_residual_jacobian(pb2_aux* h, const double* Z, double* delta, double* vals, int space) {
   if (!h || !Z) return fail(PB2_EINVAL, "pb2_aux_residual_jacobian: null argument");
-  PB2_CUDA(cudaSetDevice(h->d.device));
+  DeviceGuard guard_13(h->d.device);
   if (space == PB2_DEVICE) {
     int rc = aux_launch(h, Z, nullptr, delta, vals, nullptr, h->stream);
     if (rc) return rc;
@@ -1057,7 +1144,7 @@ int pb2_aux_residual_jacobian(pb2_aux* h, const double* Z, double* delta, double
 
 int pb2_aux_hess_lagrangian(pb2_aux* h, const double* mu, double* vals, int space) {
   if (!h || !mu || !vals) return fail(PB2_EINVAL, "pb2_aux_hess_lagrangian: null argument");
-  PB2_CUDA(cudaSetDevice(h->d.device));
+  DeviceGuard guard_14(h->d.device);
   if (h->n_der <= 0) return PB2_OK;
   pb2::AuxParams p = h->p;
   p.n_rows = h->n_der;   // time rows have no second derivatives
@@ -1219,18 +1306,17 @@ int pb2_obj_create(const pb2_obj_desc* desc, pb2_obj** out) {
     return fail(PB2_ENODEVICE, "pb2_obj_create: no CUDA device (this library has no CPU path)");
   }
   if (d.device < 0 || d.device >= ndev) return fail(PB2_EINVAL, "pb2_obj_create: bad device ordinal");
-  PB2_CUDA(cudaSetDevice(d.device));
+  DeviceGuard guard_15(d.device);
   pb2_obj* h = new (std::nothrow) pb2_obj();
   if (!h) return fail(PB2_ENOMEM, "pb2_obj_create: out of memory");
   h->K = d.K; h->D = d.D; h->dt_off = d.dt_off; h->n_terms = d.n_terms; h->n_regs = d.n_regs; h->device = d.device;
   h->smem = 2 * (size_t)d.D * sizeof(double);
   int rc = obj_build(h, d);
-  if (!rc && h->smem > 48 * 1024) {
-    if (h->smem > 200 * 1024) rc = fail(PB2_EINVAL, "pb2_obj_create: knot column too large for shared memory");
-    else if (cudaFuncSetAttribute(pb2::knot_objective_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)h->smem) != cudaSuccess)
-      rc = fail(PB2_ECUDA, "pb2_obj_create: cudaFuncSetAttribute failed");
-  }
+  if (!rc && h->smem > 200 * 1024) rc = fail(PB2_EINVAL, "pb2_obj_create: knot column too large for shared memory");
+  // (function attribute, process-wide: always the device limit -- see pb2_create)
+  if (!rc && cudaFuncSetAttribute(pb2::knot_objective_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)kSmemLimit) != cudaSuccess)
+    rc = fail(PB2_ECUDA, "pb2_obj_create: cudaFuncSetAttribute failed");
   if (!rc && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
     rc = fail(PB2_ECUDA, "pb2_obj_create: cudaStreamCreate failed");
   if (!rc && cudaMallocHost((void**)&h->hJ, sizeof(double)) != cudaSuccess)
@@ -1245,7 +1331,7 @@ int pb2_obj_create(const pb2_obj_desc* desc, pb2_obj** out) {
 
 void pb2_obj_destroy(pb2_obj* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard_d(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* q : h->owned) cudaFree(q);
   for (double* q : {h->dZ, h->dGrad, h->dJ})
@@ -1266,13 +1352,13 @@ static int obj_launch(pb2_obj* h, const double* dZ, double* dJ, double* dgrad, c
 
 int pb2_obj_value_gradient_async(pb2_obj* h, const double* dZ, double* dJ, double* dgrad, void* stream) {
   if (!h || !dZ || !dJ) return fail(PB2_EINVAL, "pb2_obj_value_gradient_async: null argument");
-  PB2_CUDA(cudaSetDevice(h->device));
+  DeviceGuard guard_16(h->device);
   return obj_launch(h, dZ, dJ, dgrad, (cudaStream_t)stream);
 }
 
 int pb2_obj_value_gradient(pb2_obj* h, const double* Z, double* J, double* grad, int space) {
   if (!h || !Z || !J) return fail(PB2_EINVAL, "pb2_obj_value_gradient: null argument");
-  PB2_CUDA(cudaSetDevice(h->device));
+  DeviceGuard guard_17(h->device);
   if (space == PB2_DEVICE) {
     int rc = obj_launch(h, Z, J, grad, h->stream);
     if (rc) return rc;

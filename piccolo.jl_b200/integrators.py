@@ -239,23 +239,33 @@ class B200BilinearIntegrator:
             raise ValueError("datavec has the wrong length")
         return Z
 
+    @staticmethod
+    def _out(a, n, what):
+        """A caller-supplied output buffer goes straight to the C ABI: it must be exactly what the library
+        writes (contiguous float64 of the exact length), or the call would overrun it silently."""
+        if a is None:
+            return np.empty(n)
+        if not isinstance(a, np.ndarray) or a.dtype != np.float64 or a.size != n or not a.flags.c_contiguous \
+                or not a.flags.writeable:
+            raise ValueError(f"{what} must be a writeable contiguous float64 array of length {n}")
+        return a
+
     def evaluate_(self, delta, Z):
         Z = self._Z(Z)
-        if delta.size != self.dim or delta.dtype != np.float64 or not delta.flags.c_contiguous:
-            raise ValueError("delta must be a contiguous float64 vector of length B.dim")
+        delta = self._out(delta, self.dim, "delta")
         capi.check(self._lib.pb2_residual(self._h, Z.ctypes.data, delta.ctypes.data, capi.PB2_HOST))
         return delta
 
     def jacobian_values(self, Z, out=None):
         Z = self._Z(Z)
-        out = np.empty(self.nnz_jac) if out is None else out
+        out = self._out(out, self.nnz_jac, "out")
         capi.check(self._lib.pb2_jacobian(self._h, Z.ctypes.data, out.ctypes.data, capi.PB2_HOST))
         return out
 
     def residual_jacobian(self, Z, delta=None, vals=None):
         Z = self._Z(Z)
-        delta = np.empty(self.dim) if delta is None else delta
-        vals = np.empty(self.nnz_jac) if vals is None else vals
+        delta = self._out(delta, self.dim, "delta")
+        vals = self._out(vals, self.nnz_jac, "vals")
         capi.check(self._lib.pb2_residual_jacobian(self._h, Z.ctypes.data, delta.ctypes.data,
                                                    vals.ctypes.data, capi.PB2_HOST))
         return delta, vals
@@ -265,7 +275,7 @@ class B200BilinearIntegrator:
         mu = np.ascontiguousarray(mu, dtype=np.float64)
         if mu.size != self.dim:
             raise ValueError("mu must have length B.dim")
-        out = np.empty(self.nnz_hess) if out is None else out
+        out = self._out(out, self.nnz_hess, "out")
         capi.check(self._lib.pb2_hess_lagrangian(self._h, Z.ctypes.data, mu.ctypes.data,
                                                  out.ctypes.data, capi.PB2_HOST))
         return out

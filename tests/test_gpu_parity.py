@@ -455,8 +455,8 @@ def _device_resjac(B, Z, early_z=False):
 
 @pytest.mark.parametrize("K", [1000, 2, 149, 700, 1037])
 def test_single_round_kernel_every_occupancy(K, monkeypatch):
-    """knot_u8p (all knots of an SM in flight, propagator tiles first) takes every 3-qubit call with at most
-    seven knots per SM: one knot in the whole grid, one per SM, ragged slot counts, the BASELINE size and the
+    """The kernels for at most seven knots per SM (default: knot_u8q, two 256-thread CTAs per SM of at most four
+    knots each; PB2_U8Q=0: knot_u8p, one CTA per SM, propagator tiles first) take every such 3-qubit call: one knot in the whole grid, one per SM, ragged slot counts, the BASELINE size and the
     largest eligible size.  Canonical arrays through device pointers, with and without the early-Z promise,
     and compact records through the host-pointer path; the two-round kernel (PB2_U8P=0) must agree to
     rounding, the C++ port to the parity tolerances."""
@@ -477,11 +477,32 @@ def test_single_round_kernel_every_occupancy(K, monkeypatch):
     torch.cuda.synchronize()
     assert np.array_equal(dv2.cpu().numpy(), v)
     B.close()
-    monkeypatch.setenv("PB2_U8P", "0")
+    # the other kernels of this shape on the same inputs: PB2_U8Q=0 -> the one-CTA-per-SM single-round kernel
+    # (knot_u8p), additionally PB2_U8P=0 -> the persistent two-round kernel (knot_u8)
+    monkeypatch.setenv("PB2_U8Q", "0")
     B2 = make(p, "dmma")
     d2, v2 = _device_resjac(B2, Z)
     assert np.abs(d2 - d).max() < PATH_TOL and np.abs(v2 - v).max() < PATH_TOL
+    dh2, vh2 = B2.residual_jacobian(Z)
+    assert np.array_equal(d2, dh2) and np.array_equal(v2, vh2)
     B2.close()
+    monkeypatch.setenv("PB2_U8P", "0")
+    B3 = make(p, "dmma")
+    d3, v3 = _device_resjac(B3, Z)
+    assert np.abs(d3 - d).max() < PATH_TOL and np.abs(v3 - v).max() < PATH_TOL
+    B3.close()
+
+
+@pytest.mark.parametrize("K", [1300, 8000])
+def test_two_cta_kernel_many_waves(K, monkeypatch):
+    """PB2_U8Q=2 lets the two-CTAs-per-SM kernel take any size (several waves of 4-knot CTAs)."""
+    monkeypatch.setenv("PB2_U8Q", "2")
+    p, Z, mu = C.trajectory(3 if K < 5000 else 5, K)
+    B = make(p, "dmma")
+    d, v = _device_resjac(B, Z, early_z=True)
+    assert np.abs(d - CP.residual(p, Z)).max() < RES_TOL
+    assert np.abs(v - CP.jacobian_values(p, Z)).max() < JAC_TOL
+    B.close()
 
 
 def test_single_round_kernel_substeps_nan_three_drives():
