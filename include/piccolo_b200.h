@@ -145,16 +145,22 @@ int pb2_enable_peer_access(int32_t device, int32_t peer);
 void* pb2_stream(const pb2_handle* h);
 int pb2_sync(pb2_handle* h);
 
-/* Per-handle options (all default 0).
- *  PB2_OPT_EARLY_Z  the caller promises that the trajectory buffer dZ passed to the *_async entry points is
- *                   complete before the kernel enqueued immediately before the call on that stream STARTS
- *                   (true whenever Z arrives by a copy -- the Ipopt callback case -- and for back-to-back
- *                   evaluator calls on one trajectory).  The kernels are launched with programmatic stream
- *                   serialization; with this promise they load Z, build G(u_k) and run the propagator tiles
- *                   before `griddepcontrol.wait`, so consecutive callbacks overlap one launch's drain with the
- *                   next one's prologue.  Outputs are never written before the wait.  The host-pointer entry
- *                   points always have this property (the library itself copies Z on the handle's stream). */
-enum { PB2_OPT_EARLY_Z = 1 };
+/* Per-handle options (all default 0): promises of the caller about the *_async entry points.  The kernels are
+ * launched with programmatic stream serialization, i.e. their CTAs may be scheduled while the kernel enqueued
+ * immediately before on the same stream is still draining; by default they then wait for that kernel's completion
+ * (`griddepcontrol.wait`) before touching the trajectory or the outputs, which makes a call behave like any
+ * stream-ordered launch.
+ *  PB2_OPT_EARLY_Z    dZ is complete before the kernel enqueued immediately before this call STARTS (true whenever Z
+ *                     arrives by a copy -- the Ipopt callback case -- and for back-to-back evaluator calls).  The
+ *                     kernels then load Z, build G(u_k) and run their products before the dependency wait; outputs
+ *                     are still written only after it.
+ *  PB2_OPT_PIPELINED  in addition, the kernel enqueued immediately before does not ACCESS this call's output buffers
+ *                     (e.g. consecutive evaluations into different buffers, or a preceding copy): no dependency wait
+ *                     at all, so consecutive calls overlap freely (one grid's tail under the next one's products) and
+ *                     need not complete in order.  Later stream operations are ordered after both as usual.
+ * The host-pointer entry points always run in the second mode: the library itself copies Z to, and the results from,
+ * its own buffers on the handle's stream. */
+enum { PB2_OPT_EARLY_Z = 1, PB2_OPT_PIPELINED = 2 };
 int pb2_set_option(pb2_handle* h, int32_t option, int64_t value);
 
 /* ---- linear knot constraints evaluated in the same callbacks -----------------

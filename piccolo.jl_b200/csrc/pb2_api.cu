@@ -63,6 +63,18 @@ struct DeviceGuard {
 constexpr int kNT = 256;
 constexpr size_t kSmemLimit = 227 * 1024;
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION (per device), not of a handle: it is
+// always raised to everything the device allows next to the kernel's static shared memory, so that a second live
+// handle with a smaller problem can never lower the cap under an earlier handle's launches.
+template <class K>
+cudaError_t raise_dynamic_smem(K kernel) {
+  cudaFuncAttributes fa{};
+  cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+  if (e != cudaSuccess) return e;
+  const size_t room = kSmemLimit > fa.sharedSizeBytes ? kSmemLimit - fa.sharedSizeBytes : 0;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room);
+}
+
 struct LaunchCfg {
   int GS = 0, KPC = 0, gj_in_smem = 0;
   size_t smem = 0;
@@ -77,7 +89,7 @@ bool plan_generic(int order, int b, int n_b, int m, LaunchCfg& cfg) {
   for (int gj = 1; gj >= 0; --gj) {
     for (int KPC = kNT / GS; KPC >= 1; KPC /= 2) {
       size_t smem = pb2::generic_smem_bytes(order, b, n_b, m, GS, KPC, gj != 0);
-      if (smem <= kSmemLimit) {
+      if (smem + 64 <= kSmemLimit) {   // (the kernels hold a few bytes of static shared memory as well)
         cfg.GS = GS;
         cfg.KPC = KPC;
         cfg.gj_in_smem = gj;
@@ -128,7 +140,7 @@ struct pb2_handle {
   int direct_last = 1;
   int u8s = 0;             // first single-round draft (whole-knot slots), kept for A/B measurements (PB2_U8S=1)
   int u8p = 1;             // single-round kernel for <= 7 knots per SM (knot_u8p.cuh); PB2_U8P=0 disables it
-  int u8q = 1;             // small-CTA kernel (knot_u8q.cuh); PB2_U8Q=0 disables it, PB2_U8Q=2 takes every size
+  int u8q = 2;             // small-CTA kernel (knot_u8q.cuh): 2 = every size, 1 = at most 7 knots per SM, 0 = off (PB2_U8Q)
   int u8q_ns = 2;          // knots per CTA: 4 (two CTAs per SM) or 2 (four CTAs per SM); PB2_U8Q_NS
   int u8q_space = 0;       // minimum spacing (cycles) of the product phases of CTAs sharing an SM; PB2_U8Q_SPACE
   unsigned long long* dSmClock = nullptr;
@@ -137,6 +149,7 @@ struct pb2_handle {
   bool u8p_ok = false, u8p_unit = false;
   double u8p_cj[4] = {1.0, 1.0, 1.0, 1.0};
   int early_z = 0;         // PB2_OPT_EARLY_Z: device-pointer calls may read Z before the programmatic dependency wait
+  int pipelined = 0;       // PB2_OPT_PIPELINED: no dependency wait at all (outputs not shared with the preceding kernel)
   pb2::EllEntry* dEll = nullptr;
   // staging for host-pointer calls
   double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
@@ -175,7 +188,8 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
     q.nnz_jac = p.nnz_jac; q.max_sub = 4096; q.nk = (int)h->nk();
     q.zlen = p.D + p.x_off + 128;
-    q.early_z = (z_stable || h->early_z) ? 1 : 0;
+    q.early_z = (z_stable || h->early_z || h->pipelined) ? 1 : 0;
+    q.nowait = (z_stable || h->pipelined) ? 1 : 0;   // z_stable: the library's own host-pointer path (copies around the kernel)
     q.compact = compact; q.cstride = (p.m + 3) * 128;
     q.tables = h->dTablesQ; q.ell = h->dEll;
     for (int j = 0; j < 4; ++j) q.cj[j] = h->u8p_cj[j];
@@ -185,7 +199,7 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
 #endif
     const int ns = h->u8q_ns, cps = 8 / ns;   // knots per CTA, CTAs per SM
     q.space = h->u8q_space; q.sm_clock = h->dSmClock;
-    q.nowait = std::getenv("PB2_NOWAIT") ? std::atoi(std::getenv("PB2_NOWAIT")) : 0;   // EXPERIMENT
+    if (const char* env = std::getenv("PB2_NOWAIT")) q.nowait = std::atoi(env);   // (measurement knob)
     q.pro = std::getenv("PB2_U8Q_PRO") ? std::atoi(std::getenv("PB2_U8Q_PRO")) : 3000;
     unsigned grid;
     if (q.nk <= 7 * h->n_sm) {
@@ -538,12 +552,8 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
   for (int q = 1; q <= pb2::kMaxDeg; ++q) theta[q] = theta_bound(q);
   PB2_CUDA_H(cudaMemcpyToSymbol(pb2::c_theta, theta, sizeof(theta)));
 
-  // the attribute belongs to the FUNCTION, not to this handle: always the device limit, so that a second live
-  // handle with a smaller generator can never lower the cap under an earlier handle's launches
-  PB2_CUDA_H(cudaFuncSetAttribute(pb2::knot_generic_kernel<1, kNT>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-  PB2_CUDA_H(cudaFuncSetAttribute(pb2::knot_generic_kernel<2, kNT>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    PB2_CUDA_H(raise_dynamic_smem(pb2::knot_generic_kernel<1, kNT>));
+  PB2_CUDA_H(raise_dynamic_smem(pb2::knot_generic_kernel<2, kNT>));
   if (h->alg == PB2_ALG_DMMA) {
     const size_t ng = h->plan.gfrag.size() * sizeof(double), ne = h->plan.ell.size() * sizeof(pb2::EllEntry);
     const size_t nn = h->plan.norms.size() * sizeof(double);
@@ -583,6 +593,7 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     if (const char* env = std::getenv("PB2_U8Q_NS")) h->u8q_ns = std::atoi(env) == 2 ? 2 : 4;
     if (const char* env = std::getenv("PB2_U8Q_SPACE")) h->u8q_space = std::atoi(env);
     if (const char* env = std::getenv("PB2_EARLY_Z")) h->early_z = std::atoi(env);
+    if (const char* env = std::getenv("PB2_PIPELINED")) h->pipelined = std::atoi(env);
     h->u8_ok = h->plan.iso && d.b == 16 && d.n_b == 8 && d.m >= 1 && d.m <= 6 && !std::getenv("PB2_NO_U8");
     if (h->u8_ok) {
       PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8_kernel(h->plan.W), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -834,6 +845,7 @@ int pb2_set_option(pb2_handle* h, int32_t option, int64_t value) {
   if (check(h)) return PB2_EINVAL;
   switch (option) {
     case PB2_OPT_EARLY_Z: h->early_z = value != 0; return PB2_OK;
+    case PB2_OPT_PIPELINED: h->pipelined = value != 0; return PB2_OK;
     default: return fail(PB2_EINVAL, "pb2_set_option: unknown option");
   }
 }
@@ -1314,8 +1326,7 @@ int pb2_obj_create(const pb2_obj_desc* desc, pb2_obj** out) {
   int rc = obj_build(h, d);
   if (!rc && h->smem > 200 * 1024) rc = fail(PB2_EINVAL, "pb2_obj_create: knot column too large for shared memory");
   // (function attribute, process-wide: always the device limit -- see pb2_create)
-  if (!rc && cudaFuncSetAttribute(pb2::knot_objective_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)kSmemLimit) != cudaSuccess)
+  if (!rc && raise_dynamic_smem(pb2::knot_objective_kernel) != cudaSuccess)
     rc = fail(PB2_ECUDA, "pb2_obj_create: cudaFuncSetAttribute failed");
   if (!rc && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
     rc = fail(PB2_ECUDA, "pb2_obj_create: cudaStreamCreate failed");

@@ -244,6 +244,32 @@ def test_full_size_c5_eight_thousand_knots():
     B.close()
 
 
+def test_live_handles_are_independent():
+    """Distinct handles are independent (include/piccolo_b200.h): creating a handle for a small problem while a
+    handle for a large one is alive must not disturb the large one's launches (the dynamic shared-memory cap is a
+    property of the kernel function, not of a handle), and no entry point changes the caller's current device."""
+    import torch
+    pL, ZL, muL = C.trajectory(3, 12)            # unitary 16 x 16: the jet kernels need > 48 KB of shared memory
+    BL = make(pL, "generic")
+    hL = BL.hessian_values(ZL, muL)
+    dL, vL = BL.residual_jacobian(ZL)
+    pS, ZS, muS = C.trajectory(6, 9)             # a small ket problem, created while the first handle is alive
+    BS = make(pS, "generic")
+    check_all(pS, ZS, muS, BS)
+    assert np.array_equal(BL.hessian_values(ZL, muL), hL)
+    d2, v2 = BL.residual_jacobian(ZL)
+    assert np.array_equal(d2, dL) and np.array_equal(v2, vL)
+    trajS = pb.NamedTrajectory(ZS, {"ψ̃": range(pS.x_off, pS.x_off + pS.n_x), "Δt": range(pS.dt_off, pS.dt_off + 1),
+                                    "u": range(pS.u_off, pS.u_off + pS.m)})
+    J = pb.QuadraticRegularizer("u", trajS, 1.0)          # objective handle: same kind of function attribute
+    J.value_gradient(ZS)
+    assert np.array_equal(BL.hessian_values(ZL, muL), hL)
+    J.close()
+    assert torch.cuda.current_device() == 0
+    BS.close()
+    BL.close()
+
+
 def test_device_pointer_api_matches_host_api():
     import torch
     p, Z, mu = C.trajectory(2, 40)
@@ -440,11 +466,13 @@ def test_u8_kernel_substeps_nan_and_many_knots():
     B.close()
 
 
-def _device_resjac(B, Z, early_z=False):
+def _device_resjac(B, Z, early_z=False, pipelined=False):
     """The canonical (non-compact) device-pointer call, as the benchmark issues it."""
     import torch
     if early_z:
         B.set_option("early_z", 1)
+    if pipelined:
+        B.set_option("pipelined", 1)
     dZ = torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda()
     dd = torch.full((B.dim,), np.nan, dtype=torch.float64, device="cuda")
     dv = torch.full((B.nnz_jac,), np.nan, dtype=torch.float64, device="cuda")
@@ -468,6 +496,9 @@ def test_single_round_kernel_every_occupancy(K, monkeypatch):
     assert np.abs(v - CP.jacobian_values(p, Z)).max() < JAC_TOL
     d_e, v_e = _device_resjac(B, Z, early_z=True)
     assert np.array_equal(d, d_e) and np.array_equal(v, v_e)
+    d_p, v_p = _device_resjac(B, Z, pipelined=True)                 # no dependency wait at all
+    assert np.array_equal(d, d_p) and np.array_equal(v, v_p)
+    B.set_option("pipelined", 0)
     dh, vh = B.residual_jacobian(Z)                                 # compact records + host expansion
     assert np.array_equal(d, dh) and np.array_equal(v, vh)
     import torch
@@ -491,6 +522,28 @@ def test_single_round_kernel_every_occupancy(K, monkeypatch):
     d3, v3 = _device_resjac(B3, Z)
     assert np.abs(d3 - d).max() < PATH_TOL and np.abs(v3 - v).max() < PATH_TOL
     B3.close()
+
+
+def test_pipelined_back_to_back_launches():
+    """PB2_OPT_PIPELINED: consecutive calls into distinct buffers overlap freely (no dependency wait) and may
+    complete out of order; after a stream synchronize every one of them holds the same, correct arrays."""
+    import torch
+    p, Z, mu = C.trajectory(3, 1000)
+    B = make(p, "dmma")
+    d0, v0 = _device_resjac(B, Z)
+    B.set_option("pipelined", 1)
+    st = torch.cuda.Stream()
+    n = 24
+    dZ = [torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda() for _ in range(n)]
+    dd = [torch.full((B.dim,), np.nan, dtype=torch.float64, device="cuda") for _ in range(n)]
+    dv = [torch.full((B.nnz_jac,), np.nan, dtype=torch.float64, device="cuda") for _ in range(n)]
+    torch.cuda.synchronize()
+    for i in range(n):
+        B.residual_jacobian_device(dZ[i], dd[i], dv[i], st.cuda_stream)
+    st.synchronize()
+    for i in range(n):
+        assert np.array_equal(dd[i].cpu().numpy(), d0) and np.array_equal(dv[i].cpu().numpy(), v0)
+    B.close()
 
 
 @pytest.mark.parametrize("K", [1300, 8000])

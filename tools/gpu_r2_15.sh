@@ -1,8 +1,8 @@
 #!/bin/bash
 O=gpurun_out/r2; mkdir -p $O
-( time python -m pytest tests -m gpu -x -q -k "single_round or two_cta or u8 or full_size or compact or sharded_integrator_single" ) > $O/pytest_17.log 2>&1
-( time PB2_U8Q_NS=4 python -m pytest tests -m gpu -x -q -k "single_round or two_cta" ) > $O/pytest_17b.log 2>&1
-tail -n 5 $O/pytest_17.log; tail -n 5 $O/pytest_17b.log
+( time python -m pytest tests -m gpu -x -q  ) > $O/pytest_18.log 2>&1
+( time PB2_U8Q_NS=4 python -m pytest tests -m gpu -x -q -k "single_round or two_cta" ) > $O/pytest_18b.log 2>&1
+tail -n 5 $O/pytest_18.log; tail -n 5 $O/pytest_18b.log
 run() { # name, env...
   n=$1; shift
   env "$@" python bench.py --steps 20 --warmup 5 --no-cpu > $O/bench_$n.json 2> $O/bench_$n.err
