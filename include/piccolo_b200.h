@@ -168,10 +168,15 @@ int pb2_set_option(pb2_handle* h, int32_t option, int64_t value);
  *   src/control/templates/smooth_pulse_problem.jl:267-275, spline_pulse_problem.jl:363-366)
  * time consistency: t_{k+1} - t_k - dt_k   (applied by DirectTrajOpt when :t and :dt exist,
  *   smooth_pulse_problem.jl:277).
+ * TimeStepsAllEqualConstraint: dt_{k+1} - dt_k, k = 1 .. K-1   (pushed by the templates when
+ *   piccolo_options.timesteps_all_equal is set: src/control/templates/_problem_templates.jl:175-180; the
+ *   constraint type lives in DirectTrajOpt, source absent -- row form "parity unpinned", the reference's
+ *   solutions satisfy it exactly).
  * One handle evaluates every pair of a trajectory in one launch.  Row order: pair-major (the order
  * given), knot-major inside a pair, component fastest; time rows last.  Jacobian values per
  * derivative row: d x_k[i] (-1), d xdot_k[i] (-dt_k), d dt_k (-xdot_k[i]), d x_{k+1}[i] (+1); per
- * time row: d t_k (-1), d dt_k (-1), d t_{k+1} (+1).  Hessian of sum mu.r: one entry per derivative
+ * time row: d t_k (-1), d dt_k (-1), d t_{k+1} (+1); per equal-timestep row (they come last): d dt_k (-1),
+ * d dt_{k+1} (+1).  Hessian of sum mu.r: one entry per derivative
  * row, (xdot_k[i], dt_k) = -mu (upper triangle).  Rows / columns 1-based like pb2_structure_*;
  * rows are local to this handle (the caller offsets them into the NLP's constraint vector). */
 #define PB2_AUX_MAX_PAIRS 8
@@ -182,6 +187,7 @@ typedef struct pb2_aux_desc {
   int32_t n_pairs;
   int32_t x_off[PB2_AUX_MAX_PAIRS], xdot_off[PB2_AUX_MAX_PAIRS], dim[PB2_AUX_MAX_PAIRS];
   int32_t device;
+  int32_t timesteps_all_equal;         /* != 0: K-1 rows dt_{k+1} - dt_k after the time rows */
 } pb2_aux_desc;
 typedef struct pb2_aux pb2_aux;
 int pb2_aux_create(const pb2_aux_desc* desc, pb2_aux** out);

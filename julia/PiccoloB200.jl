@@ -185,6 +185,7 @@ struct PB2AuxDesc
     K::Int32; D::Int32; dt_off::Int32; t_off::Int32; global_dim::Int32; n_pairs::Int32
     x_off::NTuple{8,Int32}; xdot_off::NTuple{8,Int32}; dim::NTuple{8,Int32}
     device::Int32
+    timesteps_all_equal::Int32      # != 0: K-1 rows Δt_{k+1} - Δt_k (TimeStepsAllEqualConstraint, _problem_templates.jl:175-180)
 end
 
 mutable struct B200DerivativeIntegrator <: AbstractIntegrator
@@ -196,7 +197,7 @@ mutable struct B200DerivativeIntegrator <: AbstractIntegrator
         comps = traj.components
         pad(v) = ntuple(i -> i == 1 ? Int32(v) : Int32(0), 8)
         desc = PB2AuxDesc(traj.N, traj.dim, first(comps[traj.timestep]) - 1, -1, traj.global_dim, 1,
-                          pad(first(comps[x]) - 1), pad(first(comps[ẋ]) - 1), pad(length(comps[x])), device)
+                          pad(first(comps[x]) - 1), pad(first(comps[ẋ]) - 1), pad(length(comps[x])), device, 0)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:pb2_aux_create, LIB), Cint, (Ref{PB2AuxDesc}, Ref{Ptr{Cvoid}}), desc, h))
         B = new(h[], x, ẋ, ccall((:pb2_aux_dim, LIB), Int64, (Ptr{Cvoid},), h[]))

@@ -55,6 +55,7 @@ class pb2_aux_desc(ctypes.Structure):
         ("global_dim", ctypes.c_int32), ("n_pairs", ctypes.c_int32),
         ("x_off", ctypes.c_int32 * PB2_AUX_MAX_PAIRS), ("xdot_off", ctypes.c_int32 * PB2_AUX_MAX_PAIRS),
         ("dim", ctypes.c_int32 * PB2_AUX_MAX_PAIRS), ("device", ctypes.c_int32),
+        ("timesteps_all_equal", ctypes.c_int32),
     ]
 
 

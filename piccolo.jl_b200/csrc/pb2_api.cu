@@ -1008,7 +1008,7 @@ struct pb2_aux {
   pb2::AuxParams p{};
   cudaStream_t stream = nullptr;
   double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
-  int64_t n_der = 0, n_time = 0;
+  int64_t n_der = 0, n_time = 0, n_eq = 0;
 };
 
 int pb2_aux_create(const pb2_aux_desc* desc, pb2_aux** out) {
@@ -1045,7 +1045,9 @@ int pb2_aux_create(const pb2_aux_desc* desc, pb2_aux** out) {
   p.row0[d.n_pairs] = row;
   h->n_der = row;
   h->n_time = d.t_off >= 0 ? nk : 0;
-  p.n_rows = row + h->n_time;
+  h->n_eq = d.timesteps_all_equal ? nk : 0;
+  p.row_eq = row + h->n_time;
+  p.n_rows = row + h->n_time + h->n_eq;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return fail(PB2_ECUDA, "pb2_aux_create: cudaStreamCreate failed");
@@ -1066,7 +1068,7 @@ void pb2_aux_destroy(pb2_aux* h) {
 }
 
 int64_t pb2_aux_dim(const pb2_aux* h) { return h ? h->p.n_rows : -1; }
-int64_t pb2_aux_nnz_jac(const pb2_aux* h) { return h ? 4 * h->n_der + 3 * h->n_time : -1; }
+int64_t pb2_aux_nnz_jac(const pb2_aux* h) { return h ? 4 * h->n_der + 3 * h->n_time + 2 * h->n_eq : -1; }
 int64_t pb2_aux_nnz_hess(const pb2_aux* h) { return h ? h->n_der : -1; }
 
 int pb2_aux_structure_jac(const pb2_aux* h, int64_t* rows, int64_t* cols) {
@@ -1089,6 +1091,12 @@ int pb2_aux_structure_jac(const pb2_aux* h, int64_t* rows, int64_t* cols) {
       rows[o] = r; cols[o++] = c0 + d.t_off;
       rows[o] = r; cols[o++] = c0 + d.dt_off;
       rows[o] = r; cols[o++] = c0 + D + d.t_off;
+    }
+  if (d.timesteps_all_equal)
+    for (int64_t k = 0; k < nk; ++k, ++r) {
+      const int64_t c0 = k * D + 1;
+      rows[o] = r; cols[o++] = c0 + d.dt_off;
+      rows[o] = r; cols[o++] = c0 + D + d.dt_off;
     }
   return PB2_OK;
 }

@@ -321,16 +321,20 @@ class B200BilinearIntegrator:
 
 
 class B200KnotLinearConstraints:
-    """Every ``DerivativeIntegrator(x, xdot, traj)`` of a problem plus the time-consistency constraint,
+    """Every ``DerivativeIntegrator(x, xdot, traj)`` of a problem plus the time-consistency constraint and
+    ``TimeStepsAllEqualConstraint`` (``timesteps_all_equal=True``, _problem_templates.jl:175-180),
     evaluated by one launch (smooth_pulse_problem.jl:267-277; include/piccolo_b200.h for the orders)."""
 
-    def __init__(self, traj, pairs=(("u", "du"), ("du", "ddu")), time_consistency=True, device=0):
+    def __init__(self, traj, pairs=(("u", "du"), ("du", "ddu")), time_consistency=True, device=0,
+                 timesteps_all_equal=False):
         self._lib = capi.load_library()
         comps = traj.components
         d = capi.pb2_aux_desc()
         d.K, d.D, d.dt_off = traj.N, traj.dim, comps[traj.timestep].start
         d.t_off = comps["t"].start if (time_consistency and "t" in comps) else -1
         d.global_dim, d.n_pairs, d.device = traj.global_dim, len(pairs), device
+        d.timesteps_all_equal = 1 if timesteps_all_equal else 0
+        self.timesteps_all_equal = bool(timesteps_all_equal)
         if len(pairs) > capi.PB2_AUX_MAX_PAIRS:
             raise ValueError("too many derivative pairs")
         self.pairs = []

@@ -735,6 +735,23 @@ def test_linear_knot_constraints_match_oracle_and_golden():
     d, _ = L.residual_jacobian(Zg)
     assert np.abs(d).max() < 1e-12          # the reference's converged solution satisfies them
     L.close()
+    # TimeStepsAllEqualConstraint rows (_problem_templates.jl:175-180) ride along in the same launch
+    for Z in (Zg, np.asfortranarray(Zg + 0.01 * rng.standard_normal(Zg.shape))):
+        traj = pb.NamedTrajectory.smooth_pulse_layout(Z, p.n_x, p.m, "Ũ⃗")
+        L = pb.B200KnotLinearConstraints(traj, timesteps_all_equal=True)
+        assert L.dim == (2 * p.m + 2) * (p.K - 1) and L.nnz_jac == (8 * p.m + 3 + 2) * (p.K - 1)
+        d, v = L.residual_jacobian(Z)
+        assert np.array_equal(d, LN.residual(Z, L.pairs, L.dt_off, L.t_off, dt_all_equal=True))
+        ro, co, vo = LN.jacobian(Z, L.pairs, L.dt_off, L.t_off, dt_all_equal=True)
+        r, c = L.jacobian_structure()
+        assert np.array_equal(r, ro) and np.array_equal(c, co) and np.array_equal(v, vo)
+        mu = rng.standard_normal(L.dim)
+        hr, hc, hv = LN.hessian(Z, mu, L.pairs, L.dt_off)     # linear rows add no second derivatives
+        r, c = L.hessian_structure()
+        assert np.array_equal(r, hr) and np.array_equal(c, hc) and np.array_equal(L.hessian_values(mu), hv)
+        if Z is Zg:
+            assert np.all(d[-(p.K - 1):] == 0.0)     # the reference solved with timesteps_all_equal: exactly equal steps
+        L.close()
 
 
 def test_multi_ket_and_sampling_integrator_vectors():

@@ -181,6 +181,15 @@ def test_linear_knot_constraints_on_reference_golden():
     d2 = (f(1e-3) - 2 * f(0.0) + f(-1e-3)) / 1e-6
     z = dZ.reshape(-1, order="F")
     assert abs(2 * np.sum(hv * z[hr - 1] * z[hc - 1]) - d2) < 1e-6 * max(1.0, abs(d2))
+    # TimeStepsAllEqualConstraint (_problem_templates.jl:175-180): the reference solved this problem with
+    # timesteps_all_equal on, and its solution has exactly equal steps; Jacobian rows against differences
+    re = LN.residual(Z, pairs, n_x, n_x + 1, dt_all_equal=True)
+    assert re.size == r.size + p.K - 1 and np.all(re[r.size:] == 0.0) and np.array_equal(re[:r.size], r)
+    rows, cols, vals = LN.jacobian(Z, pairs, n_x, n_x + 1, dt_all_equal=True)
+    fd = (LN.residual(Z + h * dZ, pairs, n_x, n_x + 1, True) - LN.residual(Z - h * dZ, pairs, n_x, n_x + 1, True)) / (2 * h)
+    jv = np.zeros(re.size)
+    np.add.at(jv, rows - 1, vals * dZ.reshape(-1, order="F")[cols - 1])
+    assert np.abs(jv - fd).max() < 1e-8 and rows.max() == re.size
 
 
 def test_multi_ket_golden_is_a_valid_input():
