@@ -79,6 +79,13 @@ typedef struct pb2_desc {
   int32_t algorithm;   /* PB2_ALG_* */
   const double* G0;    /* host, b*b column-major: drift generator (dissipators folded in) */
   const double* Gj;    /* host, m blocks of b*b column-major: drive generators */
+  int32_t t_off;       /* time-dependent handles: 0-based row of the knot time t (else ignored) */
+  int32_t time_dependent; /* != 0: Ghat(u, t) = G0 + sum_j c_j(t) u_j G_j  (ModulatedDrive over LinearDrive,
+                          src/quantum/systems/drives.jl:342-388; TimeDependentBilinearIntegrator,
+                          src/control/integrators.jl:38-46).  The Jacobian gains one column per knot, d/d t_k
+                          (the LAST n_x values of the knot's segment, col = k D + t_off); the coefficients
+                          c_j(t_k), c_j'(t_k) are supplied by pb2_set_time_coefficients before each evaluation.
+                          The Lagrangian Hessian and the compact / exchange forms are not available. */
 } pb2_desc;
 
 typedef struct pb2_handle pb2_handle;
@@ -162,6 +169,24 @@ int pb2_sync(pb2_handle* h);
  * its own buffers on the handle's stream. */
 enum { PB2_OPT_EARLY_Z = 1, PB2_OPT_PIPELINED = 2 };
 int pb2_set_option(pb2_handle* h, int32_t option, int64_t value);
+
+/* Time-dependent handles: the modulation values at the trajectory's CURRENT time row, c[j + m k] = c_j(t_k) and
+ * cdot[j + m k] = c_j'(t_k), j < m, k < K (the host evaluates the closures: m x K numbers per callback).  They
+ * stay in force until the next call.  space = PB2_HOST or PB2_DEVICE. */
+int pb2_set_time_coefficients(pb2_handle* h, const double* c, const double* cdot, int space);
+
+/* ---- rollout of the trajectory's piecewise-constant controls -----------------------
+ * x_1 = x0 (NULL: the first state column of Z), x_{k+1} = exp(dt_k Ghat(u_k)) x_k: what `rollout!(qtraj, pulse)`
+ * (src/quantum/trajectories/rollouts_extensions.jl:46-92) produces at the knot times for the zero-order-hold pulse
+ * that `sync_trajectory!` (src/control/problems.jl:186-208) extracts from the optimizer's trajectory -- the reference
+ * integrates the ODE adaptively (abstol = reltol = 1e-8), here every interval is propagated exactly by the E_k the
+ * knot kernels compute.  states: n_x * K doubles, column k = state at knot k (may be NULL).
+ * out3: [0] rollout_divergence (problems.jl:336-356) = ||x_K^rollout - x_K^collocation||_2 / max(||x_K^collocation||_2, 1),
+ * [1] the numerator, [2] ||x_K^collocation||_2 (so a caller can stack several state components as the reference
+ * does for multi-state trajectories); may be NULL.  Terminal fidelities of the rolled-out state are the objective
+ * terms of pb2_obj_* evaluated on `states`. */
+int pb2_rollout(pb2_handle* h, const double* Z, const double* x0, double* states, double* out3, int space);
+int pb2_rollout_async(pb2_handle* h, const double* dZ, const double* dx0, double* dstates, double* dout3, void* stream);
 
 /* ---- linear knot constraints evaluated in the same callbacks -----------------
  * DerivativeIntegrator(x, xdot, traj): r_k = x_{k+1} - x_k - dt_k xdot_k   (u -> du, du -> ddu;

@@ -25,7 +25,8 @@ from .generators import (  # noqa: F401
 from .integrators import (  # noqa: F401
     B200BilinearIntegrator, B200KnotLinearConstraints, BilinearIntegrator, DensityTrajectory, KetTrajectory,
     MultiDensityTrajectory, MultiKetTrajectory, NamedTrajectory, OpenQuantumSystem, QuantumSystem, SamplingTrajectory, UnitaryTrajectory,
-    eval_jacobian, evaluate_, hessian_of_lagrangian, hessian_structure, jacobian_structure, test_integrator,
+    eval_jacobian, evaluate_, hessian_of_lagrangian, hessian_structure, jacobian_structure, rollout_divergence,
+    test_integrator,
 )
 from .objectives import (  # noqa: F401
     B200Objective, CoherentKetInfidelityObjective, DensityMatrixInfidelityObjective,

@@ -25,7 +25,8 @@ SYMBOLS = [
     "pb2_aux_structure_jac", "pb2_aux_structure_hess", "pb2_aux_residual_jacobian", "pb2_aux_hess_lagrangian",
     "pb2_aux_residual_jacobian_async",
     "pb2_obj_create", "pb2_obj_destroy", "pb2_obj_value_gradient", "pb2_obj_value_gradient_async",
-    "pb2_stream", "pb2_sync", "pb2_set_option", "pb2_host_alloc", "pb2_host_free", "pb2_launch_count",
+    "pb2_stream", "pb2_sync", "pb2_set_option", "pb2_rollout", "pb2_rollout_async",
+    "pb2_set_time_coefficients", "pb2_host_alloc", "pb2_host_free", "pb2_launch_count",
 ]
 
 
@@ -42,7 +43,7 @@ class pb2_desc(ctypes.Structure):
         ("x_off", ctypes.c_int32), ("dt_off", ctypes.c_int32), ("u_off", ctypes.c_int32),
         ("global_dim", ctypes.c_int32), ("knot0", ctypes.c_int64), ("device", ctypes.c_int32),
         ("algorithm", ctypes.c_int32), ("G0", ctypes.POINTER(ctypes.c_double)),
-        ("Gj", ctypes.POINTER(ctypes.c_double)),
+        ("Gj", ctypes.POINTER(ctypes.c_double)), ("t_off", ctypes.c_int32), ("time_dependent", ctypes.c_int32),
     ]
 
 
@@ -131,6 +132,9 @@ def load_library():
     L.pb2_residual_jacobian_exchange_async.argtypes = [H, vp, ctypes.c_int32, ctypes.c_int32,
                                                        ctypes.POINTER(vp), ctypes.c_int64, vp]
     L.pb2_set_option.argtypes = [H, ctypes.c_int32, ctypes.c_int64]
+    L.pb2_set_time_coefficients.argtypes = [H, vp, vp, ctypes.c_int]
+    L.pb2_rollout.argtypes = [H, vp, vp, vp, vp, ctypes.c_int]
+    L.pb2_rollout_async.argtypes = [H, vp, vp, vp, vp, vp]
     L.pb2_stream.argtypes = [H]
     L.pb2_stream.restype = ctypes.c_void_p
     L.pb2_aux_create.argtypes = [ctypes.POINTER(pb2_aux_desc), ctypes.POINTER(H)]

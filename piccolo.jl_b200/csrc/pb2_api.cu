@@ -26,6 +26,8 @@
 #include "knot_u8h.cuh"
 #include "knot_aux.cuh"
 #include "knot_objective.cuh"
+#include "knot_rollout.cuh"
+#include "knot_td.cuh"
 #include "knot_u8s.cuh"
 #include "knot_u8p.cuh"
 #include "knot_u8q.cuh"
@@ -125,6 +127,9 @@ struct pb2_handle {
   double* dNorms = nullptr;
   double* dTab = nullptr;
   double *dComp = nullptr, *hComp = nullptr;   // compact records: device buffer and pinned landing zone
+  double *dCoef = nullptr, *dCoefDot = nullptr, *dZs = nullptr;   // time-dependent handles: c, c', scaled trajectory
+  bool coef_set = false;
+  double *dRoJac = nullptr, *dRoStates = nullptr, *dRoX0 = nullptr, *dRoOut = nullptr;   // rollout scratch (lazy)
   cudaEvent_t chunk_ev[16] = {};
   double* dTables = nullptr;   // [gfrag | norms (even) | theta | 1/k!] contiguous, the u8 kernels' smem order
   long long* dTrace = nullptr;
@@ -159,7 +164,7 @@ struct pb2_handle {
 
   int n_x() const { return d.b * d.n_b; }
   int64_t nk() const { return (int64_t)d.K - 1; }
-  int nnz_jac_knot() const { return d.n_b * d.b * d.b + n_x() * d.m + 2 * n_x(); }
+  int nnz_jac_knot() const { return d.n_b * d.b * d.b + n_x() * d.m + 2 * n_x() + (d.time_dependent ? n_x() : 0); }
   int nnz_hess_knot() const { return n_x() * d.m + n_x() + d.m * (d.m + 1) / 2 + d.m + 1; }
 };
 
@@ -174,8 +179,37 @@ pb2::KnotParams make_params(const pb2_handle* h) {
   return p;
 }
 
+int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, int compact,
+                       int n_peers, double* const* peers, int self, int z_stable);
+
+// Every residual / Jacobian launch goes through here.  Time-dependent handles: scale the drive rows by c_j(t_k),
+// run the knot kernels on the scaled copy, then apply the chain rule to the finished values (knot_td.cuh).
 int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, int compact = 0,
                   int n_peers = 0, double* const* peers = nullptr, int self = 0, int z_stable = 0) {
+  if (!h->d.time_dependent) return launch_resjac_core(h, dZ, ddelta, djac, st, compact, n_peers, peers, self, z_stable);
+  if (h->nk() <= 0) return PB2_OK;
+  if (compact || n_peers) return fail(PB2_EINVAL, "time-dependent handles do not produce compact records");
+  if (!h->coef_set) return fail(PB2_EINVAL, "time-dependent handle: call pb2_set_time_coefficients before evaluating");
+  pb2::TdParams t{};
+  t.K = h->d.K; t.D = h->d.D; t.m = h->d.m; t.n_x = h->n_x(); t.u_off = h->d.u_off;
+  t.nnz_jac = h->nnz_jac_knot(); t.o_jets = (long long)h->d.n_b * h->d.b * h->d.b;
+  t.c = h->dCoef; t.cdot = h->dCoefDot; t.Z = dZ; t.Zs = h->dZs; t.jac = djac;
+  const long long n = (long long)t.K * t.D;
+  pb2::td_scale_controls_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, st>>>(t);
+  PB2_CUDA(cudaGetLastError());
+  // (the scaled copy is produced by the kernel just enqueued: the knot kernels must not read it early)
+  int rc = launch_resjac_core(h, h->dZs, ddelta, djac, st, 0, 0, nullptr, 0, 0);
+  if (rc) return rc;
+  if (djac) {
+    pb2::td_finish_kernel<<<(unsigned)std::min<int64_t>(h->nk(), 148 * 8), 128, 0, st>>>(t);
+    PB2_CUDA(cudaGetLastError());
+  }
+  h->launches += djac ? 2 : 1;
+  return PB2_OK;
+}
+
+int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, int compact,
+                       int n_peers, double* const* peers, int self, int z_stable) {
   if (h->nk() <= 0) return PB2_OK;
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.delta = ddelta; p.jac = djac;
@@ -188,8 +222,10 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
     q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
     q.nnz_jac = p.nnz_jac; q.max_sub = 4096; q.nk = (int)h->nk();
     q.zlen = p.D + p.x_off + 128;
-    q.early_z = (z_stable || h->early_z || h->pipelined) ? 1 : 0;
-    q.nowait = (z_stable || h->pipelined) ? 1 : 0;   // z_stable: the library's own host-pointer path (copies around the kernel)
+    // (time-dependent handles read a scaled copy written by the kernel enqueued just before: never early)
+    const bool td = h->d.time_dependent != 0;
+    q.early_z = (!td && (z_stable || h->early_z || h->pipelined)) ? 1 : 0;
+    q.nowait = (!td && (z_stable || h->pipelined)) ? 1 : 0;   // z_stable: the library's own host-pointer path
     q.compact = compact; q.cstride = (p.m + 3) * 128;
     q.tables = h->dTablesQ; q.ell = h->dEll;
     for (int j = 0; j < 4; ++j) q.cj[j] = h->u8p_cj[j];
@@ -378,6 +414,9 @@ int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac,
 
 int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhess, cudaStream_t st) {
   if (h->nk() <= 0) return PB2_OK;
+  if (h->d.time_dependent)
+    return fail(PB2_EINVAL, "the Lagrangian Hessian of a time-dependent handle is not available (use the reference's "
+                            "integrator or a quasi-Newton Hessian)");
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.mu = dmu; p.hess = dhess;
   if (h->u8h_ok && ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)dmu % 16 == 0) && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
@@ -489,6 +528,8 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
   if (!inside(d.x_off, n_x) || !inside(d.dt_off, 1) || !inside(d.u_off, d.m))
     return fail(PB2_EINVAL, "pb2_create: component offsets outside the knot column");
   if (!d.G0 || (d.m > 0 && !d.Gj)) return fail(PB2_EINVAL, "pb2_create: null generator");
+  if (d.time_dependent && !inside(d.t_off, 1))
+    return fail(PB2_EINVAL, "pb2_create: time-dependent handle needs the row of the knot time inside the knot column");
   if (d.algorithm < PB2_ALG_AUTO || d.algorithm > PB2_ALG_DMMA)
     return fail(PB2_EINVAL, "pb2_create: bad algorithm");
 
@@ -541,6 +582,12 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
   } while (0)
 
   PB2_CUDA_H(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  if (d.time_dependent) {
+    const size_t nc = std::max<size_t>(1, (size_t)d.m * d.K);
+    PB2_CUDA_H(cudaMalloc(&h->dCoef, nc * sizeof(double)));
+    PB2_CUDA_H(cudaMalloc(&h->dCoefDot, nc * sizeof(double)));
+    PB2_CUDA_H(cudaMalloc(&h->dZs, (size_t)d.D * d.K * sizeof(double)));
+  }
   PB2_CUDA_H(cudaMalloc(&h->dG0, bb * sizeof(double)));
   PB2_CUDA_H(cudaMalloc(&h->dGj, std::max<size_t>(1, (size_t)d.m * bb) * sizeof(double)));
   PB2_CUDA_H(cudaMemcpy(h->dG0, h->G0.data(), bb * sizeof(double), cudaMemcpyHostToDevice));
@@ -671,6 +718,10 @@ void pb2_destroy(pb2_handle* h) {
   if (h->dTablesP) cudaFree(h->dTablesP);
   if (h->dTablesQ) cudaFree(h->dTablesQ);
   if (h->dSmClock) cudaFree(h->dSmClock);
+  for (double* q : {h->dCoef, h->dCoefDot, h->dZs})
+    if (q) cudaFree(q);
+  for (double* q : {h->dRoJac, h->dRoStates, h->dRoX0, h->dRoOut})
+    if (q) cudaFree(q);
   if (h->dComp) cudaFree(h->dComp);
   if (h->hComp) cudaFreeHost(h->hComp);
   for (cudaEvent_t e : h->chunk_ev)
@@ -740,6 +791,11 @@ int pb2_structure_jac(const pb2_handle* h, int64_t* rows, int64_t* cols) {
       rows[o] = r0 + i;
       cols[o++] = c0 + D + d.x_off + i;
     }
+    if (d.time_dependent)
+      for (int64_t i = 0; i < n_x; ++i) {
+        rows[o] = r0 + i;
+        cols[o++] = c0 + d.t_off;
+      }
   }
   return PB2_OK;
 }
@@ -784,7 +840,7 @@ int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu
 }
 
 int64_t pb2_compact_stride(const pb2_handle* h) {
-  if (!h || !(h->alg == PB2_ALG_DMMA && h->u8_ok) || (h->d.D % 2) || (h->d.x_off % 2)) return 0;
+  if (!h || !(h->alg == PB2_ALG_DMMA && h->u8_ok) || (h->d.D % 2) || (h->d.x_off % 2) || h->d.time_dependent) return 0;
   return (int64_t)(h->d.m + 3) * 128;
 }
 
@@ -986,6 +1042,75 @@ int pb2_hess_lagrangian(pb2_handle* h, const double* Z, const double* mu, double
   if ((rc = stage_out_begin(h, vals, h->hHess, h->dHess, nH, po))) return rc;
   PB2_CUDA(cudaStreamSynchronize(h->stream));
   stage_out_finish(po);
+  return PB2_OK;
+}
+
+int pb2_set_time_coefficients(pb2_handle* h, const double* c, const double* cdot, int space) {
+  if (check(h)) return PB2_EINVAL;
+  if (!h->d.time_dependent) return fail(PB2_EINVAL, "pb2_set_time_coefficients: not a time-dependent handle");
+  if (!c || !cdot || (space != PB2_HOST && space != PB2_DEVICE)) return fail(PB2_EINVAL, "pb2_set_time_coefficients: bad argument");
+  DeviceGuard guard(h->d.device);
+  const size_t n = (size_t)h->d.m * h->d.K * sizeof(double);
+  const cudaMemcpyKind kind = space == PB2_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  if (n) {
+    PB2_CUDA(cudaMemcpyAsync(h->dCoef, c, n, kind, h->stream));
+    PB2_CUDA(cudaMemcpyAsync(h->dCoefDot, cdot, n, kind, h->stream));
+    PB2_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  h->coef_set = true;
+  return PB2_OK;
+}
+
+// ---- rollout (knot_rollout.cuh) --------------------------------------------------------------------------
+static int launch_rollout(pb2_handle* h, const double* dZ, const double* dx0, double* dstates, double* dout3,
+                          cudaStream_t st, int z_stable) {
+  const size_t nJ = (size_t)std::max<int64_t>(pb2_nnz_jac(h), 1);
+  if (!h->dRoJac) PB2_CUDA(cudaMalloc(&h->dRoJac, nJ * sizeof(double)));
+  // the propagators: one residual + Jacobian launch (Jacobian values only) into the handle's scratch
+  int rc = launch_resjac(h, dZ, nullptr, h->dRoJac, st, 0, 0, nullptr, 0, z_stable);
+  if (rc) return rc;
+  pb2::RolloutParams q{};
+  q.b = h->d.b; q.n_b = h->d.n_b; q.K = h->d.K; q.D = h->d.D; q.x_off = h->d.x_off;
+  q.nnz_jac = h->nnz_jac_knot();
+  q.jac = h->dRoJac; q.Z = dZ; q.x0 = dx0; q.states = dstates; q.out = dout3;
+  const size_t smem = pb2::rollout_smem_bytes(q.b, q.n_b);
+  if (smem > 48 * 1024) return fail(PB2_EINVAL, "pb2_rollout: state too large for the shared-memory chain");
+  pb2::knot_rollout_kernel<<<1, pb2::kRolloutThreads, smem, st>>>(q);
+  PB2_CUDA(cudaGetLastError());
+  h->launches++;
+  return PB2_OK;
+}
+
+int pb2_rollout_async(pb2_handle* h, const double* dZ, const double* dx0, double* dstates, double* dout3, void* stream) {
+  if (check(h)) return PB2_EINVAL;
+  if (!dZ) return fail(PB2_EINVAL, "pb2_rollout_async: null Z");
+  DeviceGuard guard(h->d.device);
+  return launch_rollout(h, dZ, dx0, dstates, dout3, (cudaStream_t)stream, 0);
+}
+
+int pb2_rollout(pb2_handle* h, const double* Z, const double* x0, double* states, double* out3, int space) {
+  if (check(h)) return PB2_EINVAL;
+  if (!Z) return fail(PB2_EINVAL, "pb2_rollout: null Z");
+  DeviceGuard guard(h->d.device);
+  if (space == PB2_DEVICE) {
+    int rc = launch_rollout(h, Z, x0, states, out3, h->stream, 0);
+    if (rc) return rc;
+    PB2_CUDA(cudaStreamSynchronize(h->stream));
+    return PB2_OK;
+  }
+  if (space != PB2_HOST) return fail(PB2_EINVAL, "pb2_rollout: bad space");
+  const size_t nZ = (size_t)h->d.D * h->d.K, nx = (size_t)h->n_x(), nS = nx * (size_t)h->d.K;
+  int rc;
+  if ((rc = ensure(&h->dZ, &h->hZ, nZ))) return rc;
+  if (!h->dRoStates) PB2_CUDA(cudaMalloc(&h->dRoStates, std::max<size_t>(nS, 1) * sizeof(double)));
+  if (!h->dRoX0) PB2_CUDA(cudaMalloc(&h->dRoX0, std::max<size_t>(nx, 1) * sizeof(double)));
+  if (!h->dRoOut) PB2_CUDA(cudaMalloc(&h->dRoOut, 3 * sizeof(double)));
+  if ((rc = stage_in(h, Z, h->hZ, h->dZ, nZ))) return rc;
+  if (x0) PB2_CUDA(cudaMemcpyAsync(h->dRoX0, x0, nx * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = launch_rollout(h, h->dZ, x0 ? h->dRoX0 : nullptr, h->dRoStates, h->dRoOut, h->stream, 1))) return rc;
+  if (states) PB2_CUDA(cudaMemcpyAsync(states, h->dRoStates, nS * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (out3) PB2_CUDA(cudaMemcpyAsync(out3, h->dRoOut, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PB2_CUDA(cudaStreamSynchronize(h->stream));
   return PB2_OK;
 }
 

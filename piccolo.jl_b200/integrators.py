@@ -27,7 +27,19 @@ class QuantumSystem:
 
     def __post_init__(self):
         self.H_drift = np.asarray(self.H_drift, dtype=complex)
-        self.H_drives = [np.asarray(H, dtype=complex) for H in self.H_drives]
+        # a drive may be given as (H, modulation) -- the reference's `H => t -> c(t)` pair, which becomes
+        # ModulatedDrive(LinearDrive(H, j), c) and makes the system time dependent (quantum_systems.jl:540-597)
+        drives, self.modulations, self.modulation_derivs = [], [], []
+        for d in self.H_drives:
+            if isinstance(d, tuple):
+                drives.append(d[0])
+                self.modulations.append(d[1])
+                self.modulation_derivs.append(d[2] if len(d) > 2 else None)
+            else:
+                drives.append(d)
+                self.modulations.append(None)
+                self.modulation_derivs.append(None)
+        self.H_drives = [np.asarray(H, dtype=complex) for H in drives]
         if not np.allclose(self.H_drift, self.H_drift.conj().T):
             raise ValueError("Drift Hamiltonian H_drift is not Hermitian")
         for i, H in enumerate(self.H_drives):
@@ -36,6 +48,15 @@ class QuantumSystem:
 
     levels = property(lambda self: self.H_drift.shape[0])
     n_drives = property(lambda self: len(self.H_drives))
+    time_dependent = property(lambda self: any(f is not None for f in self.modulations))
+
+    def td_kwargs(self, traj):
+        """Extra constructor arguments of a time-dependent system's integrators (integrators.jl:38-46: the
+        reference passes the :t component to TimeDependentBilinearIntegrator)."""
+        if not self.time_dependent:
+            return {}
+        return dict(t_off=traj.components["t"].start, modulations=self.modulations,
+                    modulation_derivs=self.modulation_derivs)
 
     def G_parts(self):
         return gen.G(self.H_drift), [gen.G(H) for H in self.H_drives]
@@ -176,7 +197,8 @@ class B200BilinearIntegrator:
     """
 
     def __init__(self, kind, G_drift, G_drives, *, K, D, x_off, dt_off, u_off, x_name="x",
-                 u_name="u", device=0, algorithm="auto", knot0=0, global_dim=0, n_states=1):
+                 u_name="u", device=0, algorithm="auto", knot0=0, global_dim=0, n_states=1,
+                 t_off=None, modulations=None, modulation_derivs=None):
         self._lib = capi.load_library()
         G0 = np.asfortranarray(G_drift, dtype=np.float64)
         b = G0.shape[0]
@@ -193,10 +215,25 @@ class B200BilinearIntegrator:
         self.x_name, self.u_name = x_name, u_name
         self.knot0, self.global_dim, self.device = int(knot0), int(global_dim), int(device)
         self._G0, self._Gj = G0, Gj  # keep alive during create
+        # time-dependent systems (TimeDependentBilinearIntegrator, integrators.jl:38-46): drive j is
+        # ModulatedDrive(LinearDrive(H_j, j), c_j) (drives.jl:342-388); c_j = None means unmodulated
+        self.modulations = list(modulations) if modulations is not None else None
+        self.time_dependent = self.modulations is not None and any(f is not None for f in self.modulations)
+        if self.time_dependent:
+            if t_off is None or len(self.modulations) != m:
+                raise ValueError("a time-dependent integrator needs t_off and one modulation (or None) per drive")
+            derivs = list(modulation_derivs) if modulation_derivs is not None else [None] * m
+
+            def numeric(f):     # ForwardDiff in the reference; here a central difference of the closure
+                return lambda t: (f(t + 1e-6) - f(t - 1e-6)) / 2e-6
+            self.modulation_derivs = [None if f is None else (g if g is not None else numeric(f))
+                                      for f, g in zip(self.modulations, derivs)]
+        self.t_off = int(t_off) if t_off is not None else 0
         d = capi.pb2_desc(capi.KIND[kind], b, self.n_b, m, self.K, self.D, self.x_off, self.dt_off,
                           self.u_off, self.global_dim, self.knot0, self.device, capi.ALG[algorithm],
                           G0.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                          Gj.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+                          Gj.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                          self.t_off, 1 if self.time_dependent else 0)
         h = ctypes.c_void_p()
         capi.check(self._lib.pb2_create(ctypes.byref(d), ctypes.byref(h)))
         self._h = h
@@ -237,7 +274,27 @@ class B200BilinearIntegrator:
             Z = np.asfortranarray(Z)
         elif Z.size != self.D * self.K:
             raise ValueError("datavec has the wrong length")
+        if self.time_dependent:
+            self.set_time_coefficients(*self.time_coefficients(Z))
         return Z
+
+    def time_coefficients(self, Z):
+        """c[j, k] = c_j(t_k), c'[j, k]: the modulation closures evaluated at the trajectory's current time row
+        (what the Julia shim does before each callback; the closures themselves cannot cross the C ABI)."""
+        t = np.asarray(Z).reshape(-1, order="F")[self.t_off::self.D][:self.K] if np.ndim(Z) == 1 else np.asarray(Z)[self.t_off, :]
+        c, cd = np.ones((self.m, self.K), order="F"), np.zeros((self.m, self.K), order="F")
+        for j, (f, g) in enumerate(zip(self.modulations, self.modulation_derivs)):
+            if f is not None:
+                c[j, :] = [f(tk) for tk in t]
+                cd[j, :] = [g(tk) for tk in t]
+        return c, cd
+
+    def set_time_coefficients(self, c, cdot):
+        c = np.asfortranarray(c, dtype=np.float64)
+        cdot = np.asfortranarray(cdot, dtype=np.float64)
+        if c.shape != (self.m, self.K) or cdot.shape != (self.m, self.K):
+            raise ValueError("coefficient tables are m x K")
+        capi.check(self._lib.pb2_set_time_coefficients(self._h, c.ctypes.data, cdot.ctypes.data, capi.PB2_HOST))
 
     @staticmethod
     def _out(a, n, what):
@@ -307,6 +364,31 @@ class B200BilinearIntegrator:
     def expand_compact_device(self, dcompact, n_knots, ddelta, dvals, stream=None):
         capi.check(self._lib.pb2_expand_compact_async(self._h, _as_ptr(dcompact), int(n_knots), _as_ptr(ddelta),
                                                       _as_ptr(dvals), _as_ptr(stream)))
+
+    # -- rollout of the piecewise-constant controls (rollout!, sync_trajectory!, rollout_divergence) ---------
+    def rollout(self, Z, x0=None):
+        """States at every knot from x_1 = x0 (default: Z's first state column), x_{k+1} = exp(Δt_k Ĝ(u_k)) x_k
+        (rollouts_extensions.jl:46-92 for the zero-order-hold pulse of sync_trajectory!, problems.jl:186-208).
+        Returns (states [x_dim x K, Fortran order], rollout_divergence, ||Δx_K||, ||x_K^collocation||)."""
+        Z = self._Z(Z)
+        states = np.empty((self.x_dim, self.K), order="F")
+        out3 = np.empty(3)
+        x0p = None
+        if x0 is not None:
+            x0 = np.ascontiguousarray(x0, dtype=np.float64)
+            if x0.size != self.x_dim:
+                raise ValueError("x0 must have length B.x_dim")
+            x0p = x0.ctypes.data
+        capi.check(self._lib.pb2_rollout(self._h, Z.ctypes.data, x0p, states.ctypes.data, out3.ctypes.data, capi.PB2_HOST))
+        return states, float(out3[0]), float(out3[1]), float(out3[2])
+
+    def rollout_divergence(self, Z, x0=None):
+        """rollout_divergence(qcp)  (problems.jl:336-356) for this integrator's state component."""
+        return self.rollout(Z, x0)[1]
+
+    def rollout_device(self, dZ, dx0, dstates, dout3, stream=None):
+        capi.check(self._lib.pb2_rollout_async(self._h, _as_ptr(dZ), _as_ptr(dx0), _as_ptr(dstates), _as_ptr(dout3),
+                                               _as_ptr(stream)))
 
     def sync(self):
         capi.check(self._lib.pb2_sync(self._h))
@@ -418,7 +500,7 @@ def BilinearIntegrator(qtraj, traj_or_N, traj=None, **kw):
             return B200BilinearIntegrator(
                 qtraj.kind, G0, Gj, K=traj.N, D=traj.dim, x_off=blocks[0].start, dt_off=comps[traj.timestep].start,
                 u_off=comps["u"].start, x_name="+".join(names), global_dim=traj.global_dim,
-                n_states=len(blocks), **kw)
+                n_states=len(blocks), **sys_.td_kwargs(traj), **kw)
 
         if multi:
             return fuse(qtraj.state_names, qtraj.system)
@@ -437,7 +519,7 @@ def BilinearIntegrator(qtraj, traj_or_N, traj=None, **kw):
             out.append(B200BilinearIntegrator(
                 qtraj.kind, G0, Gj, K=traj.N, D=traj.dim, x_off=comps[name].start,
                 dt_off=comps[traj.timestep].start, u_off=comps["u"].start, x_name=name,
-                global_dim=traj.global_dim, **kw))
+                global_dim=traj.global_dim, **sys_.td_kwargs(traj), **kw))
         return out
     if traj is None:
         raise TypeError("pass the NamedTrajectory that defines the knot layout")
@@ -448,7 +530,8 @@ def BilinearIntegrator(qtraj, traj_or_N, traj=None, **kw):
     x = comps[qtraj.state_name]
     return B200BilinearIntegrator(
         qtraj.kind, G0, Gj, K=traj.N, D=traj.dim, x_off=x.start, dt_off=comps[traj.timestep].start,
-        u_off=comps["u"].start, x_name=qtraj.state_name, global_dim=traj.global_dim, **kw)
+        u_off=comps["u"].start, x_name=qtraj.state_name, global_dim=traj.global_dim,
+        **qtraj.system.td_kwargs(traj), **kw)
 
 
 # free functions with the reference's names ------------------------------------------------
@@ -482,6 +565,18 @@ def hessian_of_lagrangian(B, traj, mu):
     vals = B.hessian_values(traj, mu)
     n = B.D * B.K + B.global_dim
     return sp.coo_matrix((vals, (rows - 1, cols - 1)), shape=(n, n))
+
+
+def rollout_divergence(integrators, traj):
+    """rollout_divergence(qcp) over a vector of state integrators (multi-state trajectories: the 2-norm of the
+    stacked difference over the 2-norm of the stacked collocation state, problems.jl:341-356)."""
+    Bs = integrators if isinstance(integrators, (list, tuple)) else [integrators]
+    sq_d = sq_c = 0.0
+    for B in Bs:
+        _, _, nd, nc = B.rollout(traj)
+        sq_d += nd * nd
+        sq_c += nc * nc
+    return np.sqrt(sq_d) / max(np.sqrt(sq_c), 1.0)
 
 
 def test_integrator(B, traj, atol=1e-3, h=1e-5, seed=0):

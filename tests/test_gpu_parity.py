@@ -754,6 +754,102 @@ def test_linear_knot_constraints_match_oracle_and_golden():
         L.close()
 
 
+@pytest.mark.parametrize("cfg,K", [(2, 40), (3, 300), (6, 33), (1, 20)])
+def test_time_dependent_drives_match_oracle(cfg, K):
+    """carrier-modulated drives (TimeDependentBilinearIntegrator, integrators.jl:38-46, with
+    ModulatedDrive coefficients c_j(t) u_j, drives.jl:342-388): residual, Jacobian with the chain rule through
+    c_j(t_k) and the extra d/d t_k column, COO structure, on every kernel family (3-qubit, general tensor-core,
+    jets); constant modulations reproduce the time-independent handle bit for bit."""
+    from oracle import knot_td as TD
+    p, Z, mu = C.trajectory(cfg, K)
+    t_off = p.dt_off + 1
+    Z[t_off, :] = np.cumsum(np.r_[0, Z[p.dt_off, :-1]]) + 0.3
+    w = [1.3, 0.7, 2.1, None, 0.4, 1.9][:p.m]
+    mods = [(lambda t, w=w_: np.cos(w * t)) if w_ else None for w_ in w]
+    dmods = [(lambda t, w=w_: -w * np.sin(w * t)) if w_ else None for w_ in w]
+    c, cd = TD.coefficients(p, Z, t_off, mods, dmods)
+    ro, co = TD.jacobian_structure(p, t_off)
+    for alg in algorithms(p):
+        B = make(p, alg, t_off=t_off, modulations=mods, modulation_derivs=dmods)
+        assert B.time_dependent and B.nnz_jac == (p.K - 1) * TD.nnz_jac_knot(p)
+        d, v = B.residual_jacobian(Z)
+        assert np.abs(d - TD.residual(p, Z, c)).max() < RES_TOL
+        assert np.abs(v - TD.jacobian_values(p, Z, c, cd)).max() < JAC_TOL
+        r, cc = B.jacobian_structure()
+        assert np.array_equal(r, ro) and np.array_equal(cc, co)
+        d2 = np.empty(B.dim)
+        B.evaluate_(d2, Z)
+        assert np.abs(d2 - d).max() < PATH_TOL
+        with pytest.raises(pb.PB2Error):
+            B.hessian_values(Z, mu)                       # not available for time-dependent handles
+        S, eps, _, _ = B.rollout(Z)                        # the rollout uses the same modulated propagators
+        assert np.isfinite(S).all()
+        B.close()
+    # numeric derivative of the closures (the default when no derivative is given): same values to 1e-8
+    B = make(p, "auto", t_off=t_off, modulations=mods)
+    d, v = B.residual_jacobian(Z)
+    assert np.abs(v - TD.jacobian_values(p, Z, c, cd)).max() < 1e-7
+    B.close()
+    # through the reference-style dispatch: QuantumSystem with (H, modulation) drive pairs
+    if cfg == 1:
+        X, Zp = np.array([[0, 1], [1, 0]]), np.diag([1.0, -1.0])
+        sys_ = pb.QuantumSystem(Zp, [(X, mods[0], dmods[0])], [1.0])
+        assert sys_.time_dependent
+        traj = pb.NamedTrajectory.smooth_pulse_layout(Z, p.n_x, p.m, "Ũ⃗")
+        Bq = pb.BilinearIntegrator(pb.UnitaryTrajectory(sys_), traj)
+        assert Bq.time_dependent
+        dq, vq = Bq.residual_jacobian(traj)
+        assert np.abs(dq - TD.residual(p, Z, c)).max() < RES_TOL and np.abs(vq - TD.jacobian_values(p, Z, c, cd)).max() < JAC_TOL
+        Bq.close()
+
+
+def test_rollout_matches_expm_chain():
+    """rollout of the piecewise-constant controls (rollout! / sync_trajectory!), terminal fidelity
+    and rollout_divergence on the device against the SciPy expm chain: the reference's converged C2 solution
+    (fidelity 0.99999999847 after rollout), C3 at full size, a ket and a Lindblad density problem."""
+    import torch
+    from oracle import rollout as RO
+    from oracle import objectives as OB
+    p, Zg = GU.load("two_qubit_zoh")
+    B = make(p)
+    S, eps, nd, nc = B.rollout(Zg)
+    So = RO.rollout(p, Zg)
+    assert np.abs(S - So).max() < 1e-10
+    eo, ndo, nco = RO.divergence(p, Zg, So)
+    assert abs(eps - eo) < 1e-12 and abs(nd - ndo) < 1e-12 and abs(nc - nco) < 1e-12 and eps < 1e-9
+    assert np.abs(S - Zg[:p.n_x]).max() < 1e-9            # the optimizer's states ARE the rollout for this solution
+    CX = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], complex)
+    Zr = Zg.copy(order="F")
+    Zr[:p.n_x, :] = S                                    # fidelity(qtraj) after sync_trajectory!: the loss on the rollout
+    traj = pb.NamedTrajectory.smooth_pulse_layout(Zr, p.n_x, p.m, "Ũ⃗")
+    J = pb.UnitaryInfidelityObjective(CX, "Ũ⃗", traj, Q=1.0)
+    val, _ = J.value_gradient(Zr)
+    assert abs((1.0 - val) - 0.9999999985) < 5e-10
+    assert abs(val - OB.unitary_infidelity(So[:, -1], CX, 1.0)[0]) < 1e-12
+    J.close()
+    assert abs(pb.rollout_divergence(B, Zg) - eo) < 1e-12
+    B.close()
+    for cfg, K in ((3, 1000), (6, 64), (4, 120), (1, 50)):
+        p, Z, mu = C.trajectory(cfg, K)
+        B = make(p)
+        x0 = Z[p.x_off:p.x_off + p.n_x, 0] * 0.5 + 0.1
+        for xi in (None, x0):
+            S, eps, nd, nc = B.rollout(Z, xi)
+            So = RO.rollout(p, Z, xi)
+            assert np.abs(S - So).max() < 1e-10
+            eo, ndo, nco = RO.divergence(p, Z, So)
+            assert abs(eps - eo) < 1e-10 and abs(nd - ndo) < 1e-10 and abs(nc - nco) < 1e-12
+        # device-pointer form
+        dZ = torch.from_numpy(Z.reshape(-1, order="F").copy()).cuda()
+        dS = torch.full((p.n_x * p.K,), np.nan, dtype=torch.float64, device="cuda")
+        do = torch.zeros(3, dtype=torch.float64, device="cuda")
+        B.rollout_device(dZ, None, dS, do, None)
+        torch.cuda.synchronize()
+        S0, e0, _, _ = B.rollout(Z)
+        assert np.array_equal(dS.cpu().numpy().reshape(p.n_x, p.K, order="F"), S0) and do[0].item() == e0
+        B.close()
+
+
 def test_multi_ket_and_sampling_integrator_vectors():
     """Row a4: one integrator per state block / ensemble member, all sharing the control rows
     (integrators.jl:102-117, 134-226).  Multi-ket on the reference's own MultiKetTrajectory solution."""

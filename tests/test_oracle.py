@@ -192,6 +192,61 @@ def test_linear_knot_constraints_on_reference_golden():
     assert np.abs(jv - fd).max() < 1e-8 and rows.max() == re.size
 
 
+def test_time_dependent_oracle_jacobian_against_differences():
+    """Carrier-modulated drives (TimeDependentBilinearIntegrator, integrators.jl:38-46; ModulatedDrive,
+    drives.jl:342-388): the restated Jacobian, the d/d t_k column included, against central differences of the
+    restated residual; with constant modulations the restatement reduces to the time-independent one."""
+    from oracle import configs as C
+    from oracle import knot as KN
+    from oracle import knot_td as TD
+    p, Z, mu = C.trajectory(2, 8)
+    t_off = p.dt_off + 1
+    Z[t_off, :] = np.cumsum(np.r_[0, Z[p.dt_off, :-1]]) + 0.3
+    w = [1.3, 0.7, 2.1, None]
+    mods = [(lambda t, w=w_: np.cos(w * t)) if w_ else None for w_ in w]
+    dmods = [(lambda t, w=w_: -w * np.sin(w * t)) if w_ else None for w_ in w]
+    c, cd = TD.coefficients(p, Z, t_off, mods, dmods)
+    r = TD.residual(p, Z, c)
+    rows, cols = TD.jacobian_structure(p, t_off)
+    vals = TD.jacobian_values(p, Z, c, cd)
+    assert rows.size == vals.size == (p.K - 1) * (p.nnz_jac_knot + p.n_x)
+    rng = np.random.default_rng(0)
+    dZ, h = rng.standard_normal(Z.shape), 1e-6
+
+    def res(Zz):
+        return TD.residual(p, Zz, TD.coefficients(p, Zz, t_off, mods, dmods)[0])
+    fd = (res(Z + h * dZ) - res(Z - h * dZ)) / (2 * h)
+    jv = np.zeros(r.size)
+    np.add.at(jv, rows - 1, vals * dZ.reshape(-1, order="F")[cols - 1])
+    assert np.abs(jv - fd).max() < 1e-7
+    one = [None] * p.m
+    c1, cd1 = TD.coefficients(p, Z, t_off, one, one)
+    assert np.array_equal(TD.residual(p, Z, c1), KN.residual(p, Z))
+    v1 = TD.jacobian_values(p, Z, c1, cd1).reshape(p.K - 1, -1)
+    assert np.array_equal(v1[:, :p.nnz_jac_knot].reshape(-1), KN.jacobian_values(p, Z)) and np.all(v1[:, p.nnz_jac_knot:] == 0)
+
+
+def test_rollout_oracle_on_reference_solution():
+    """Rolling out the controls of the reference's converged two_qubit_zoh solution from the identity reproduces
+    its stored states (each knot constraint holds to 6e-12), the divergence of problems.jl:336-356 is ~1e-10 and
+    the rolled-out terminal unitary is the CX gate to the fidelity the reference reports."""
+    from oracle import rollout as RO
+    from oracle import objectives as OB
+    from tests import golden_util as GU
+    p, Z = GU.load("two_qubit_zoh")
+    S = RO.rollout(p, Z)
+    assert S.shape == (p.n_x, p.K) and np.array_equal(S[:, 0], Z[:p.n_x, 0])
+    assert np.abs(S - Z[:p.n_x]).max() < 1e-9
+    eps, nd, nc = RO.divergence(p, Z, S)
+    assert eps < 1e-9 and abs(nc - 2.0) < 1e-8          # ||iso_vec(U)||_2 = sqrt(d) for a unitary, d = 4
+    CX = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], complex)
+    J, _ = OB.unitary_infidelity(S[:, -1], CX, 1.0)
+    assert abs((1.0 - J) - 0.9999999985) < 5e-10
+    # a different initial state: linearity of the chain
+    S2 = RO.rollout(p, Z, x0=2.0 * Z[:p.n_x, 0])
+    assert np.abs(S2 - 2.0 * S).max() < 1e-12
+
+
 def test_multi_ket_golden_is_a_valid_input():
     """The reference's MultiKetTrajectory solution (stopped at max_iter): every state block obeys its own
     dynamics constraint to the reference's solve-level tolerance, with the shared control rows."""
