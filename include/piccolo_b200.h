@@ -146,6 +146,16 @@ int pb2_expand_compact_async(pb2_handle* h, const double* dcompact, int64_t n_kn
  * across ranks before expanding / reading. */
 int pb2_residual_jacobian_exchange_async(pb2_handle* h, const double* dZ, int32_t n_ranks, int32_t rank,
                                          double* const* gather_bufs, int64_t slot_offset, void* stream);
+/* The same, closing the step inside the kernel: flag_offset (doubles, 16-byte aligned, beyond the records) locates
+ * 16 64-bit words inside EVERY gather buffer (8 arrival words and two counters; zero-initialised by the caller once).  The knot whose record
+ * leaves last writes this rank's word on every peer (release, system scope) and waits for every peer's word here,
+ * so when the call's kernel completes all ranks' records of this step are in gather_bufs[rank]: no barrier kernel
+ * follows.  Every rank must use its gather buffers in the same order (the words carry a per-buffer use counter);
+ * consecutive steps must use different gather buffers (a rank may run a step ahead of a slower one), and two calls
+ * on the same buffer must not overlap. */
+int pb2_residual_jacobian_exchange_sync_async(pb2_handle* h, const double* dZ, int32_t n_ranks, int32_t rank,
+                                              double* const* gather_bufs, int64_t slot_offset, int64_t flag_offset,
+                                              void* stream);
 /* cudaDeviceEnablePeerAccess(device -> peer) (idempotent); needed once before kernels on `device`
  * write into memory that lives on `peer` */
 int pb2_enable_peer_access(int32_t device, int32_t peer);

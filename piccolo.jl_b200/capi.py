@@ -20,7 +20,7 @@ SYMBOLS = [
     "pb2_structure_hess", "pb2_residual", "pb2_jacobian", "pb2_residual_jacobian",
     "pb2_hess_lagrangian", "pb2_residual_jacobian_async", "pb2_hess_lagrangian_async",
     "pb2_compact_stride", "pb2_residual_jacobian_compact_async", "pb2_expand_compact_async",
-    "pb2_residual_jacobian_exchange_async", "pb2_enable_peer_access",
+    "pb2_residual_jacobian_exchange_async", "pb2_residual_jacobian_exchange_sync_async", "pb2_enable_peer_access",
     "pb2_aux_create", "pb2_aux_destroy", "pb2_aux_dim", "pb2_aux_nnz_jac", "pb2_aux_nnz_hess",
     "pb2_aux_structure_jac", "pb2_aux_structure_hess", "pb2_aux_residual_jacobian", "pb2_aux_hess_lagrangian",
     "pb2_aux_residual_jacobian_async",
@@ -135,6 +135,8 @@ def load_library():
     L.pb2_set_time_coefficients.argtypes = [H, vp, vp, ctypes.c_int]
     L.pb2_rollout.argtypes = [H, vp, vp, vp, vp, ctypes.c_int]
     L.pb2_rollout_async.argtypes = [H, vp, vp, vp, vp, vp]
+    L.pb2_residual_jacobian_exchange_sync_async.argtypes = [H, vp, ctypes.c_int32, ctypes.c_int32,
+                                                            ctypes.POINTER(vp), ctypes.c_int64, ctypes.c_int64, vp]
     L.pb2_stream.argtypes = [H]
     L.pb2_stream.restype = ctypes.c_void_p
     L.pb2_aux_create.argtypes = [ctypes.POINTER(pb2_aux_desc), ctypes.POINTER(H)]

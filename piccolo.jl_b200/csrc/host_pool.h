@@ -5,6 +5,8 @@
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
+#include <algorithm>
 #include <functional>
 #include <mutex>
 #include <thread>
@@ -42,8 +44,12 @@ class HostPool {
 
  private:
   HostPool() {
+    // PB2_HOST_THREADS = threads that take part in un-packing, the caller included (default: all cores, at most
+    // 8).  Several processes sharing one host (one rank per GPU) should divide the cores between them: the
+    // workers spin on the arrival of DMA chunks, so over-subscription costs more than it gains.
     unsigned hw = std::thread::hardware_concurrency();
     int n = hw > 1 ? (int)std::min<unsigned>(hw - 1, 7) : 0;
+    if (const char* env = std::getenv("PB2_HOST_THREADS")) n = std::max(0, std::min(63, std::atoi(env) - 1));
     for (int i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
   }
   ~HostPool() {

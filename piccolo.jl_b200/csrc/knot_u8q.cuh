@@ -40,11 +40,20 @@ struct U8qParams {
   int cstride;
   int split;              // > 0: CTAs >= split own one slot less than the others (knot = slot * gridDim + block)
   int space;              // > 0: compute phases of the CTAs sharing an SM start at least `space` cycles apart
+  int n_peers;            // > 1 (sharded run, compact records): every record also goes into the gather buffer of each
+                          // other rank, peers[r] + slot_off (+ knot * cstride), over NVLink; peers[self] is the local one
+  int self;
+  long long slot_off;     // doubles: this rank's slot inside every gather buffer (jac == peers[self] + slot_off)
+  double* peers[8];
+  long long flag_off;     // >= 0: doubles offset of 16 64-bit words inside every gather buffer (0..7 arrival words, one per
+                          // source rank; 8, 9 local counters): the grid ends with an all-to-all exchange of arrival
+                          // words, so when it completes every other rank's records of this step have landed here as
+                          // well (no separate barrier kernel)
   int nowait;             // 1: no programmatic dependency wait at all (the caller's promise: PB2_OPT_PIPELINED)
   int pro;                // typical prologue length in cycles (entry -> first product) the spacing is applied after
   unsigned long long* sm_clock;   // [512] per-SM reservation word for `space` (clock64 is one counter per SM)
   // shared-memory layout in doubles (u8q_layout)
-  int o_norm, o_tab, o_f32, o_slot, slot_stride, zpad, o_prep, o_y, o_est, o_mbar;
+  int o_norm, o_tab, o_f32, o_slot, slot_stride, zpad, o_prep, o_y, o_est, o_rec, o_mbar;
   double cj[4];           // UNIT: the common magnitude of drive generator j's nonzeros
   const double* tables;   // u8q_tables: [G fragments (m+1) 256 | norms | theta | 1/k! | float norms (8) | float theta (20)]
   const EllEntry* ell;
@@ -88,6 +97,10 @@ __device__ __noinline__ void u8q_substeps(float nrm, float th_max, int max_sub, 
 #define U8Q_STAMP(i) do { } while (0)
 #endif
 
+// Sharded runs: the knot's compact record [E columns 0..7 | jets, d/d dt | delta] is staged in shared memory by the
+// slot's two warps and leaves by ONE bulk (TMA) store per destination -- the local gather buffer and, over NVLink,
+// every other rank's (cuMem-mapped peer memory): 7 KB contiguous per transfer instead of 64-byte fragments from
+// the register layout (measured at N = 2: 290 GB/s with per-lane st.global, link rate with bulk stores).
 // warp B, one step: E product (accumulator pre-loaded with the unit columns' coefficient / c_k b_E), barrier,
 // next additive term, J_3 [, J_4]
 template <bool UNIT, bool GEN>
@@ -306,7 +319,8 @@ __global__ void __launch_bounds__(64 * NS, 8 / NS) knot_u8q_kernel(const __grid_
     const uint32_t ypub = a_y + 8u * (uint32_t)(g * 4 + q);
     const uint32_t xl = 8u * (uint32_t)p.x_off + lane_col;
     double bX[4], tX[4], tJ[2][4], accX[4];
-    double* const dT_out = jj + m * 128 + lc;
+    // (sharded runs compute d/d dt after the loop: its value goes to every rank, like the rest of the record)
+    double* const dT_out = p.n_peers > 1 ? nullptr : jj + m * 128 + lc;
     const uint32_t a_graw = a_p + 8u * (uint32_t)(256 + lane);   // the unscaled G(u) fragments (d/d dt product)
 #pragma unroll
     for (int i4 = 0; i4 < 4; ++i4) {
@@ -378,14 +392,33 @@ __global__ void __launch_bounds__(64 * NS, 8 / NS) knot_u8q_kernel(const __grid_
       for (int i4 = 0; i4 < 4; ++i4) xn[i4] = lds_f64<0>(a_z + 8u * p.D + xl + U8_OFF(i4));
     }
     const double s0 = UNIT ? -p.cj[0] * dts : -1.0, s1 = UNIT ? -p.cj[1] * dts : -1.0;
-    stg_f64x2(jj + lc, s0 * tJ[0][0], s0 * tJ[0][1]);
-    stg_f64x2(jj + lc + 8, s0 * tJ[0][2], s0 * tJ[0][3]);
-    stg_f64x2(jj + 128 + lc, s1 * tJ[1][0], s1 * tJ[1][1]);
-    stg_f64x2(jj + 128 + lc + 8, s1 * tJ[1][2], s1 * tJ[1][3]);
-    if (want_delta) {
-      double* dd = (p.compact ? jj + (m + 1) * 128 : p.delta + (size_t)k * 128) + lc;
-      stg_f64x2(dd, xn[0] - tX[0], xn[1] - tX[1]);
-      stg_f64x2(dd + 8, xn[2] - tX[2], xn[3] - tX[3]);
+    if (p.n_peers > 1) {
+      double Gr[4][2], dT[2][2];
+#pragma unroll
+      for (int s8 = 0; s8 < 8; ++s8) Gr[s8 >> 1][s8 & 1] = lds_f64<0>(a_graw + 256u * (uint32_t)s8);
+      u8_mma(dT, tX, Gr);
+      const uint32_t o = a_slot + 8u * (uint32_t)p.o_rec + 1024u + lane_col;   // jets start after the E half
+      sts_f64x2<0>(o, make_double2(s0 * tJ[0][0], s0 * tJ[0][1]));
+      sts_f64x2<64>(o, make_double2(s0 * tJ[0][2], s0 * tJ[0][3]));
+      sts_f64x2<1024>(o, make_double2(s1 * tJ[1][0], s1 * tJ[1][1]));
+      sts_f64x2<1024 + 64>(o, make_double2(s1 * tJ[1][2], s1 * tJ[1][3]));
+      const uint32_t oT = o + 1024u * (uint32_t)m;
+      sts_f64x2<0>(oT, make_double2(-dT[0][0], -dT[0][1]));
+      sts_f64x2<64>(oT, make_double2(-dT[1][0], -dT[1][1]));
+      sts_f64x2<1024>(oT, make_double2(xn[0] - tX[0], xn[1] - tX[1]));
+      sts_f64x2<1024 + 64>(oT, make_double2(xn[2] - tX[2], xn[3] - tX[3]));
+      fence_proxy_async();
+      bar_sync(bar, 64);        // warp B sends the staged record
+    } else {
+      stg_f64x2(jj + lc, s0 * tJ[0][0], s0 * tJ[0][1]);
+      stg_f64x2(jj + lc + 8, s0 * tJ[0][2], s0 * tJ[0][3]);
+      stg_f64x2(jj + 128 + lc, s1 * tJ[1][0], s1 * tJ[1][1]);
+      stg_f64x2(jj + 128 + lc + 8, s1 * tJ[1][2], s1 * tJ[1][3]);
+      if (want_delta) {
+        double* dd = (p.compact ? jj + (m + 1) * 128 : p.delta + (size_t)k * 128) + lc;
+        stg_f64x2(dd, xn[0] - tX[0], xn[1] - tX[1]);
+        stg_f64x2(dd + 8, xn[2] - tX[2], xn[3] - tX[3]);
+      }
     }
   } else {
     // ================================ warp B: E, J_3 [, J_4] ============================================
@@ -447,6 +480,57 @@ __global__ void __launch_bounds__(64 * NS, 8 / NS) knot_u8q_kernel(const __grid_
     U8Q_STAMP(5);
     // the first global writes of this warp: from here on the previous grid of the stream must be complete
     if (!p.nowait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    const double s2 = UNIT ? -p.cj[2] * dts : -1.0, s3 = UNIT ? -p.cj[3] * dts : -1.0;
+    if (p.n_peers > 1) {
+      const uint32_t a_rec = a_slot + 8u * (uint32_t)p.o_rec, o = a_rec + lane_col;
+      sts_f64x2<0>(o, make_double2(-tE[0], -tE[1]));
+      sts_f64x2<64>(o, make_double2(-tE[2], -tE[3]));
+      sts_f64x2<1024 + 2 * 1024>(o, make_double2(s2 * t[0][0], s2 * t[0][1]));
+      sts_f64x2<1024 + 2 * 1024 + 64>(o, make_double2(s2 * t[0][2], s2 * t[0][3]));
+      if (two) {
+        sts_f64x2<1024 + 3 * 1024>(o, make_double2(s3 * t[1][0], s3 * t[1][1]));
+        sts_f64x2<1024 + 3 * 1024 + 64>(o, make_double2(s3 * t[1][2], s3 * t[1][3]));
+      }
+      fence_proxy_async();
+      bar_sync(bar, 64);        // warp A's part of the record is staged as well
+      if (lane == 0) {
+        const size_t go = (size_t)k * (size_t)rec;
+        const uint32_t nbytes = 8u * (uint32_t)rec;
+        bulk_s2g(p.jac + go, a_rec, nbytes);
+        for (int r = 0; r < p.n_peers; ++r)
+          if (r != p.self) bulk_s2g(p.peers[r] + p.slot_off + go, a_rec, nbytes);
+        bulk_commit();
+        bulk_wait0();            // the remote writes are performed before the grid completes
+        if (p.flag_off >= 0) {
+          // the knot whose record leaves last closes the step: tell every rank that all of this rank's records
+          // are on their way (release: they are performed, see above), then wait for the same word from everyone
+          __threadfence_system();
+          // words 0..7: arrivals (written by the peers), 8: ticket of finished knots, 9: how often THIS buffer has
+          // been used -- the step's epoch.  Both counters live in the buffer, so launches that overlap (different
+          // buffers) never share them, and every rank derives the same epoch for the same step.
+          unsigned long long* mine = reinterpret_cast<unsigned long long*>(p.peers[p.self] + p.flag_off);
+          if (atomicAdd(mine + 8, 1ull) == (unsigned long long)(p.nk - 1)) {
+            mine[8] = 0ull;
+            const unsigned long long e = mine[9] + 1ull;
+            mine[9] = e;
+            for (int r = 0; r < p.n_peers; ++r)
+              if (r != p.self) {
+                unsigned long long* f = reinterpret_cast<unsigned long long*>(p.peers[r] + p.flag_off) + p.self;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(e) : "memory");
+              }
+            for (int r = 0; r < p.n_peers; ++r)
+              if (r != p.self) {
+                unsigned long long v;
+                do {
+                  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + r) : "memory");
+                } while (v < e);
+              }
+          }
+        }
+      }
+      U8Q_STAMP(7);
+      return;
+    }
     if (p.compact) {
       stg_f64x2(jk + lc, -tE[0], -tE[1]);
       stg_f64x2(jk + lc + 8, -tE[2], -tE[3]);
@@ -468,7 +552,6 @@ __global__ void __launch_bounds__(64 * NS, 8 / NS) knot_u8q_kernel(const __grid_
       stg_f64x2(jj + (m + 1) * 128 + 4 * lane, 1.0, 1.0);
       stg_f64x2(jj + (m + 1) * 128 + 4 * lane + 2, 1.0, 1.0);
     }
-    const double s2 = UNIT ? -p.cj[2] * dts : -1.0, s3 = UNIT ? -p.cj[3] * dts : -1.0;
     stg_f64x2(jj + 2 * 128 + lc, s2 * t[0][0], s2 * t[0][1]);
     stg_f64x2(jj + 2 * 128 + lc + 8, s2 * t[0][2], s2 * t[0][3]);
     if (two) {
@@ -494,7 +577,8 @@ inline size_t u8q_layout(U8qParams& q, int ns) {
   q.o_prep = q.zpad;
   q.o_y = q.o_prep + kU8qPrep;
   q.o_est = q.o_y + 2 * 128;
-  q.o_mbar = q.o_est + 256;
+  q.o_rec = q.o_est + 256;                                    // sharded runs: the knot's compact record, staged
+  q.o_mbar = q.o_rec + (q.n_peers > 1 ? q.cstride : 0);
   q.slot_stride = q.o_mbar + 2;
   return sizeof(double) * ((size_t)q.o_slot + (size_t)ns * q.slot_stride);
 }

@@ -149,10 +149,12 @@ struct pb2_handle {
   int u8q_ns = 2;          // knots per CTA: 4 (two CTAs per SM) or 2 (four CTAs per SM); PB2_U8Q_NS
   int u8q_space = 0;       // minimum spacing (cycles) of the product phases of CTAs sharing an SM; PB2_U8Q_SPACE
   unsigned long long* dSmClock = nullptr;
+  unsigned long long* dSyncWords = nullptr;   // [0] ticket, [1] exchange epoch (knot_u8q.cuh, in-kernel step barrier)
   double* dTablesP = nullptr;   // knot_u8p's table blob (u8p_tables)
   double* dTablesQ = nullptr;   // knot_u8q's table blob (u8q_tables)
   bool u8p_ok = false, u8p_unit = false;
   double u8p_cj[4] = {1.0, 1.0, 1.0, 1.0};
+  long long xchg_flag_off = -1;   // set around an exchange_sync launch
   int early_z = 0;         // PB2_OPT_EARLY_Z: device-pointer calls may read Z before the programmatic dependency wait
   int pipelined = 0;       // PB2_OPT_PIPELINED: no dependency wait at all (outputs not shared with the preceding kernel)
   pb2::EllEntry* dEll = nullptr;
@@ -215,7 +217,8 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
   p.Z = dZ; p.delta = ddelta; p.jac = djac;
   const bool aligned16 = ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0);
   if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8q && !h->u8s && djac && aligned16 && (p.D % 2 == 0) &&
-      (p.x_off % 2 == 0) && n_peers == 0 && (h->u8q >= 2 || h->nk() <= (int64_t)7 * h->n_sm)) {
+      (p.x_off % 2 == 0) && (n_peers == 0 || !std::getenv("PB2_U8Q_NO_PEERS")) &&
+      (h->u8q >= 2 || h->nk() <= (int64_t)7 * h->n_sm)) {
     // two 256-thread CTAs per SM, at most four knots each: one CTA's prologue and tail run underneath the
     // other one's products, and a freed half-SM goes to the next grid of the stream at once (knot_u8q.cuh)
     pb2::U8qParams q{};
@@ -227,6 +230,10 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
     q.early_z = (!td && (z_stable || h->early_z || h->pipelined)) ? 1 : 0;
     q.nowait = (!td && (z_stable || h->pipelined)) ? 1 : 0;   // z_stable: the library's own host-pointer path
     q.compact = compact; q.cstride = (p.m + 3) * 128;
+    q.n_peers = n_peers; q.self = self;
+    for (int r = 0; r < n_peers && r < 8; ++r) q.peers[r] = peers[r];
+    if (n_peers > 0) q.slot_off = (long long)(djac - peers[self]);
+    q.flag_off = n_peers > 1 ? h->xchg_flag_off : -1;
     q.tables = h->dTablesQ; q.ell = h->dEll;
     for (int j = 0; j < 4; ++j) q.cj[j] = h->u8p_cj[j];
     q.Z = dZ; q.delta = ddelta; q.jac = djac;
@@ -667,6 +674,8 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
           PB2_CUDA_H(cudaMalloc(&h->dTablesQ, bq.size() * sizeof(double)));
           PB2_CUDA_H(cudaMemcpy(h->dTablesQ, bq.data(), bq.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
+        PB2_CUDA_H(cudaMalloc(&h->dSyncWords, 2 * sizeof(unsigned long long)));
+        PB2_CUDA_H(cudaMemset(h->dSyncWords, 0, 2 * sizeof(unsigned long long)));
         PB2_CUDA_H(cudaMalloc(&h->dSmClock, 512 * sizeof(unsigned long long)));
         PB2_CUDA_H(cudaMemset(h->dSmClock, 0, 512 * sizeof(unsigned long long)));
         h->u8p_ok = true;
@@ -718,6 +727,7 @@ void pb2_destroy(pb2_handle* h) {
   if (h->dTablesP) cudaFree(h->dTablesP);
   if (h->dTablesQ) cudaFree(h->dTablesQ);
   if (h->dSmClock) cudaFree(h->dSmClock);
+  if (h->dSyncWords) cudaFree(h->dSyncWords);
   for (double* q : {h->dCoef, h->dCoefDot, h->dZs})
     if (q) cudaFree(q);
   for (double* q : {h->dRoJac, h->dRoStates, h->dRoX0, h->dRoOut})
@@ -864,6 +874,20 @@ int pb2_residual_jacobian_exchange_async(pb2_handle* h, const double* dZ, int32_
       return fail(PB2_EINVAL, "pb2_residual_jacobian_exchange_async: gather buffers must be 16-byte aligned device pointers");
   DeviceGuard guard_5(h->d.device);
   return launch_resjac(h, dZ, nullptr, gather_bufs[rank] + slot_offset, (cudaStream_t)stream, 1, n_ranks, gather_bufs, rank);
+}
+
+int pb2_residual_jacobian_exchange_sync_async(pb2_handle* h, const double* dZ, int32_t n_ranks, int32_t rank,
+                                              double* const* gather_bufs, int64_t slot_offset, int64_t flag_offset,
+                                              void* stream) {
+  if (check(h)) return PB2_EINVAL;
+  if (flag_offset < 0 || (flag_offset % 2) != 0)
+    return fail(PB2_EINVAL, "pb2_residual_jacobian_exchange_sync_async: flag_offset must be a non-negative even number of doubles");
+  if (!(h->u8p_ok && h->u8q) || std::getenv("PB2_U8Q_NO_PEERS"))
+    return fail(PB2_EINVAL, "pb2_residual_jacobian_exchange_sync_async: the in-kernel step barrier needs the small-CTA kernel");
+  h->xchg_flag_off = flag_offset;
+  const int rc = pb2_residual_jacobian_exchange_async(h, dZ, n_ranks, rank, gather_bufs, slot_offset, stream);
+  h->xchg_flag_off = -1;
+  return rc;
 }
 
 int pb2_enable_peer_access(int32_t device, int32_t peer) {

@@ -361,6 +361,12 @@ class B200BilinearIntegrator:
         capi.check(self._lib.pb2_residual_jacobian_exchange_async(self._h, _as_ptr(dZ), len(gather_ptrs), int(rank), arr,
                                                                   int(slot_offset), _as_ptr(stream)))
 
+    def residual_jacobian_exchange_sync_device(self, dZ, rank, gather_ptrs, slot_offset, flag_offset, stream=None):
+        """Fused compute + exchange + step barrier in one kernel (pb2_residual_jacobian_exchange_sync_async)."""
+        arr = (ctypes.c_void_p * len(gather_ptrs))(*[int(x) for x in gather_ptrs])
+        capi.check(self._lib.pb2_residual_jacobian_exchange_sync_async(
+            self._h, _as_ptr(dZ), len(gather_ptrs), int(rank), arr, int(slot_offset), int(flag_offset), _as_ptr(stream)))
+
     def expand_compact_device(self, dcompact, n_knots, ddelta, dvals, stream=None):
         capi.check(self._lib.pb2_expand_compact_async(self._h, _as_ptr(dcompact), int(n_knots), _as_ptr(ddelta),
                                                       _as_ptr(dvals), _as_ptr(stream)))
