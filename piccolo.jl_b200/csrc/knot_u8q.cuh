@@ -497,8 +497,13 @@ __global__ void __launch_bounds__(64 * NS, 8 / NS) knot_u8q_kernel(const __grid_
         const size_t go = (size_t)k * (size_t)rec;
         const uint32_t nbytes = 8u * (uint32_t)rec;
         bulk_s2g(p.jac + go, a_rec, nbytes);
-        for (int r = 0; r < p.n_peers; ++r)
-          if (r != p.self) bulk_s2g(p.peers[r] + p.slot_off + go, a_rec, nbytes);
+        // destinations in a rank-dependent rotation (self + 1, self + 2, ...), further rotated by the knot: at any
+        // moment the ranks' transfers fan out over all peers instead of converging on one ingress port
+        for (int i = 0; i < p.n_peers - 1; ++i) {
+          int r = p.self + 1 + ((i + k) % (p.n_peers - 1));
+          if (r >= p.n_peers) r -= p.n_peers;
+          bulk_s2g(p.peers[r] + p.slot_off + go, a_rec, nbytes);
+        }
         bulk_commit();
         bulk_wait0();            // the remote writes are performed before the grid completes
         if (p.flag_off >= 0) {
