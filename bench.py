@@ -203,6 +203,7 @@ def run_ours(args):
     if world > 1 and "PB2_HOST_THREADS" not in os.environ:
         # one process per GPU on one host: divide the cores between the ranks' un-packing pools (e2e leg)
         os.environ["PB2_HOST_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
+        os.environ.setdefault("PB2_HOST_NT", "1")   # world x 23.5 MB of host arrays per step exceed the last-level cache
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
@@ -217,7 +218,14 @@ def run_ours(args):
         os.dup2(2, 1)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    p, Z, _ = C.trajectory(args.config)
+    if args.strong and world > 1:
+        # strong scaling (BASELINE config 5 as written: ONE trajectory of K knots sharded over the ranks): every rank
+        # owns (K - 1) / world knot evaluations of the same problem
+        full, _, _ = C.problem(args.config)[0], None, None
+        per = (full.K - 1 + world - 1) // world
+        p, Z, _ = C.trajectory(args.config, per + 1)
+    else:
+        p, Z, _ = C.trajectory(args.config)
     n_eval = p.K - 1
     B = pb.B200BilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off,
                                   dt_off=p.dt_off, u_off=p.u_off, device=local,
@@ -573,7 +581,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
+            "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": workload_config(p, args.config, world),
             "detail": dict(algorithm=B.algorithm, early_z=bool(early_z), pipelined=bool(pipelined),
@@ -652,6 +661,8 @@ def main():
     ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--algorithm", default="auto")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--strong", action="store_true",
+                    help="N > 1: shard ONE trajectory of the configuration's K knots over the ranks (default: K per rank)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

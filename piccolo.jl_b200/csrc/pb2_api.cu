@@ -32,6 +32,7 @@
 #include "knot_u8p.cuh"
 #include "knot_u8q.cuh"
 #include "host_pool.h"
+#include <emmintrin.h>
 
 namespace {
 
@@ -453,6 +454,19 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
   }
   h->launches++;
   return PB2_OK;
+}
+
+// Host-side replication of a landed chunk into the caller's arrays.  With PB2_HOST_NT=1 the copies use streaming
+// (non-temporal) stores: several processes un-packing 23.5 MB each per callback on one host exceed the last-level
+// cache, and a plain store first READS every destination line it is about to overwrite.
+inline void host_copy(double* dst, const double* src, size_t n, bool nt) {
+  if (!nt || ((uintptr_t)dst & 15u) != 0) {
+    std::memcpy(dst, src, n * sizeof(double));
+    return;
+  }
+  size_t i = 0;
+  for (; i + 2 <= n; i += 2) _mm_stream_pd(dst + i, _mm_loadu_pd(src + i));
+  if (i < n) dst[i] = src[i];
 }
 
 bool is_pinned_or_device(const void* ptr) {
@@ -983,8 +997,11 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
     for (auto& r : ready) r.store(0, std::memory_order_relaxed);
     std::atomic<int> failed{0};
     const double* comp = h->hComp;
+    static const bool nt = std::getenv("PB2_HOST_NT") && std::atoi(std::getenv("PB2_HOST_NT")) != 0;
     auto expand = [&](int64_t a, int64_t b) {
-      double E[256];
+      alignas(16) double E[256];
+      alignas(16) double ones[128];
+      for (double& o : ones) o = 1.0;
       for (int64_t k = a; k < b; ++k) {
         const int c = (int)(k / per);
         while (!ready[c].load(std::memory_order_acquire))
@@ -998,12 +1015,13 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
             E[(col + 8) * 16 + 8 + r] = src[col * 16 + r];
           }
         double* out = vals + k * (int64_t)nnz;
-        for (int cp = 0; cp < n_b; ++cp) std::memcpy(out + (size_t)cp * bb, E, bb * sizeof(double));
+        for (int cp = 0; cp < n_b; ++cp) host_copy(out + (size_t)cp * bb, E, bb, nt);
         out += (size_t)n_b * bb;
-        std::memcpy(out, src + 128, nJd * sizeof(double));
-        for (int i = 0; i < n_x; ++i) out[nJd + i] = 1.0;   // the constant d/dx_{k+1} identity entries
-        if (delta) std::memcpy(delta + k * n_x, src + 128 + nJd, n_x * sizeof(double));
+        host_copy(out, src + 128, nJd, nt);
+        host_copy(out + nJd, ones, n_x, nt);               // the constant d/dx_{k+1} identity entries
+        if (delta) host_copy(delta + k * n_x, src + 128 + nJd, n_x, nt);
       }
+      if (nt) _mm_sfence();
     };
     // the pool's threads start un-packing as chunks land; this thread releases the chunks, then joins in
     std::function<void(int64_t, int64_t)> fn = expand;
