@@ -86,6 +86,11 @@ typedef struct pb2_desc {
                           (the LAST n_x values of the knot's segment, col = k D + t_off); the coefficients
                           c_j(t_k), c_j'(t_k) are supplied by pb2_set_time_coefficients before each evaluation.
                           The Lagrangian Hessian and the compact / exchange forms are not available. */
+  int32_t dense_blocks;   /* != 0: the d/dx_k block of every knot is emitted as the FULL n_x x n_x block, column-major,
+                          structural zeros included (n_x^2 instead of n_b b^2 entries per knot): the layout of an
+                          integrator that does not know the I (x) E structure of the unitary case (SURVEY.md 8b and
+                          Appendix B: what DirectTrajOpt's BilinearIntegrator is believed to scatter).  A pure layout
+                          option: same kernels, one more streaming pass; compact / exchange forms unavailable. */
 } pb2_desc;
 
 typedef struct pb2_handle pb2_handle;
@@ -159,6 +164,22 @@ int pb2_residual_jacobian_exchange_sync_async(pb2_handle* h, const double* dZ, i
 /* cudaDeviceEnablePeerAccess(device -> peer) (idempotent); needed once before kernels on `device`
  * write into memory that lives on `peer` */
 int pb2_enable_peer_access(int32_t device, int32_t peer);
+/* Gather buffers without any other CUDA binding, so a host in the reference's language (Julia, one process per
+ * GPU under MPI.jl or Distributed) can shard a trajectory with this library alone:
+ *   every rank:  pb2_device_alloc(&buf, bytes, device)  (zero-filled);  pb2_ipc_export(buf, handle)
+ *   exchange the 64-byte handles through the host's own channel (MPI_Allgather, a socket, a file)
+ *   every rank:  pb2_ipc_open(handle_of_rank_r, device, &peer_buf[r])  for r != rank  (peer access is enabled
+ *                lazily by the driver);  gather_bufs = { peer_buf[0], .., buf, .., peer_buf[n-1] }
+ * and then pb2_residual_jacobian_exchange_sync_async as above.  A single process driving several GPUs needs only
+ * pb2_device_alloc per device and pb2_enable_peer_access per ordered pair.  pb2_device_copy is cudaMemcpy with
+ * cudaMemcpyDefault (host<->device, device<->device), for reading the gathered records back. */
+#define PB2_IPC_HANDLE_BYTES 64
+int pb2_device_alloc(void** ptr, int64_t bytes, int32_t device);
+int pb2_device_free(void* ptr);
+int pb2_device_copy(void* dst, const void* src, int64_t bytes);
+int pb2_ipc_export(const void* dptr, void* handle64);
+int pb2_ipc_open(const void* handle64, int32_t device, void** dptr);
+int pb2_ipc_close(void* dptr);
 void* pb2_stream(const pb2_handle* h);
 int pb2_sync(pb2_handle* h);
 
@@ -184,6 +205,32 @@ int pb2_set_option(pb2_handle* h, int32_t option, int64_t value);
  * cdot[j + m k] = c_j'(t_k), j < m, k < K (the host evaluates the closures: m x K numbers per callback).  They
  * stay in force until the next call.  space = PB2_HOST or PB2_DEVICE. */
 int pb2_set_time_coefficients(pb2_handle* h, const double* c, const double* cdot, int space);
+
+/* ---- ensembles: all members in one launch --------------------------------------------
+ * SamplingTrajectory / MultiKet / MultiDensity problems attach one integrator per ensemble member and state
+ * (src/control/integrators.jl:102-117, 134-226; sampling_problem.jl:389-395): the same knot mathematics with the
+ * member's own generator on the member's own state block, all reading the same dt / u rows.  For the small systems
+ * these problems are built from, a launch per member is pure launch latency; a batch evaluates them together
+ * (member = blockIdx.y of one grid, per-member generator tables).
+ * descs[i] must agree in kind, b, n_b, m, K, D, dt_off, u_off, global_dim, device and algorithm; x_off, G0, Gj differ.
+ * Outputs are member-major: delta [n_members][dim], vals [n_members][nnz_jac], Hessian values likewise; member i's
+ * COO structure is pb2_batch_structure_*(i) (rows local to the member, like a single handle's).
+ * Members whose kernels cannot share a launch (e.g. different sparsity widths, or the 3-qubit shape with its own
+ * kernels) are evaluated concurrently on the batch's own streams instead; results are identical. */
+typedef struct pb2_batch pb2_batch;
+int pb2_batch_create(const pb2_desc* descs, int32_t n_members, pb2_batch** out);
+void pb2_batch_destroy(pb2_batch* b);
+int32_t pb2_batch_size(const pb2_batch* b);
+int32_t pb2_batch_fused(const pb2_batch* b);      /* 1: one launch for all members */
+int64_t pb2_batch_dim(const pb2_batch* b);        /* per member */
+int64_t pb2_batch_nnz_jac(const pb2_batch* b);
+int64_t pb2_batch_nnz_hess(const pb2_batch* b);
+int pb2_batch_structure_jac(const pb2_batch* b, int32_t member, int64_t* rows, int64_t* cols);
+int pb2_batch_structure_hess(const pb2_batch* b, int32_t member, int64_t* rows, int64_t* cols);
+int pb2_batch_residual_jacobian(pb2_batch* b, const double* Z, double* delta, double* vals, int space);
+int pb2_batch_hess_lagrangian(pb2_batch* b, const double* Z, const double* mu, double* vals, int space);
+int pb2_batch_residual_jacobian_async(pb2_batch* b, const double* dZ, double* ddelta, double* dvals, void* stream);
+int pb2_batch_hess_lagrangian_async(pb2_batch* b, const double* dZ, const double* dmu, double* dvals, void* stream);
 
 /* ---- rollout of the trajectory's piecewise-constant controls -----------------------
  * x_1 = x0 (NULL: the first state column of Z), x_{k+1} = exp(dt_k Ghat(u_k)) x_k: what `rollout!(qtraj, pulse)`
@@ -295,6 +342,18 @@ void pb2_obj_destroy(pb2_obj* h);
  * handle must be ordered on one stream (use one handle per stream for concurrent evaluations). */
 int pb2_obj_value_gradient(pb2_obj* h, const double* Z, double* J, double* grad, int space);
 int pb2_obj_value_gradient_async(pb2_obj* h, const double* dZ, double* dJ, double* dgrad, void* stream);
+/* Hessian of sigma * J (Ipopt's obj_factor; eval_h adds it to the constraint Hessians of pb2_hess_lagrangian and
+ * pb2_aux_hess_lagrangian), upper triangle over the K*D trajectory entries, rows / columns 1-based, COO with
+ * duplicates allowed (Ipopt sums them).  Order: knot-major; inside a knot the term instances (dense term: the
+ * upper triangle of its rows x rows block, column-major; a_sq-only term: its diagonal; a_lin-only: nothing), then
+ * the active regularizers (diagonal, and for dt_power > 0 the (z_i, dt) entries and one (dt, dt)).
+ * |1 - F| is differentiated away from its kink: d2 = -sign(1 - F) Q d2F.  DirectTrajOpt's own layout of the
+ * objective Hessian is not in the reference tree (parity unpinned); the values are pinned by the oracle's complex
+ * form and central differences of its gradient (tests/test_oracle.py). */
+int64_t pb2_obj_nnz_hess(const pb2_obj* h);
+int pb2_obj_structure_hess(const pb2_obj* h, int64_t* rows, int64_t* cols);
+int pb2_obj_hessian(pb2_obj* h, const double* Z, double sigma, double* vals, int space);
+int pb2_obj_hessian_async(pb2_obj* h, const double* dZ, double sigma, double* dvals, void* stream);
 
 /* pinned host memory for callers that want DMA without the staging copy */
 int pb2_host_alloc(void** ptr, int64_t bytes);

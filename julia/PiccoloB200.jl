@@ -29,7 +29,12 @@ struct PB2Desc
     x_off::Int32; dt_off::Int32; u_off::Int32; global_dim::Int32
     knot0::Int64; device::Int32; algorithm::Int32
     G0::Ptr{Float64}; Gj::Ptr{Float64}
+    t_off::Int32                # 0-based row of :t (time-dependent handles only)
+    time_dependent::Int32       # != 0: drive j enters as c_j(t_k) u_j, coefficients via pb2_set_time_coefficients
+    dense_blocks::Int32         # != 0: d/dx_k as one dense x_dim × x_dim block (SURVEY.md:388)
 end
+
+const PB2_OPT_EARLY_Z, PB2_OPT_PIPELINED = Int32(1), Int32(2)
 
 check(rc) = rc == 0 || error("libpiccolo_b200: " * unsafe_string(ccall((:pb2_last_error, LIB), Cstring, ())))
 
@@ -42,8 +47,10 @@ mutable struct B200BilinearIntegrator <: AbstractIntegrator
     nnz_jac::Int
     nnz_hess::Int
     ncols::Int                    # traj.dim * traj.N + traj.global_dim   integrators.jl:780-782
+    modulations::Vector{Any}      # (c_j, ċ_j) closures of ModulatedDrive (drives.jl:342-388); empty = time-independent
     function B200BilinearIntegrator(kind, G0::Matrix{Float64}, Gj::Vector{Matrix{Float64}},
-                                    traj, x_name::Symbol, u_name::Symbol; device = 0, n_states = 1)
+                                    traj, x_name::Symbol, u_name::Symbol; device = 0, n_states = 1,
+                                    modulations = Any[], dense_blocks = false)
         b = size(G0, 1)
         # n_b contiguous state blocks share the generator: d columns of a unitary, or the n_states
         # kets / densities of a multi-state trajectory fused into one integrator (x_name = the first)
@@ -52,17 +59,34 @@ mutable struct B200BilinearIntegrator <: AbstractIntegrator
         comps = traj.components
         desc = PB2Desc(kind, b, n_b, length(Gj), traj.N, traj.dim,
                        first(comps[x_name]) - 1, first(comps[traj.timestep]) - 1, first(comps[u_name]) - 1,
-                       traj.global_dim, 0, device, 0, pointer(G0), pointer(Gjflat))
+                       traj.global_dim, 0, device, 0, pointer(G0), pointer(Gjflat),
+                       isempty(modulations) ? 0 : first(comps[:t]) - 1, isempty(modulations) ? 0 : 1,
+                       dense_blocks ? 1 : 0)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         GC.@preserve G0 Gjflat check(ccall((:pb2_create, LIB), Cint, (Ref{PB2Desc}, Ref{Ptr{Cvoid}}), desc, h))
         B = new(h[], x_name, u_name, b * n_b,
                 ccall((:pb2_dim, LIB), Int64, (Ptr{Cvoid},), h[]),
                 ccall((:pb2_nnz_jac, LIB), Int64, (Ptr{Cvoid},), h[]),
                 ccall((:pb2_nnz_hess, LIB), Int64, (Ptr{Cvoid},), h[]),
-                traj.dim * traj.N + traj.global_dim)
+                traj.dim * traj.N + traj.global_dim, collect(Any, modulations))
         finalizer(B -> ccall((:pb2_destroy, LIB), Cvoid, (Ptr{Cvoid},), B.handle), B)
         return B
     end
+end
+
+"Promise that lets consecutive *_async callbacks overlap on the GPU (include/piccolo_b200.h, pb2_set_option)."
+set_option!(B::B200BilinearIntegrator, opt::Int32, value::Integer = 1) =
+    check(ccall((:pb2_set_option, LIB), Cint, (Ptr{Cvoid}, Cint, Int64), B.handle, opt, value))
+
+# Time-dependent (carrier-modulated) drives: the closures c_j(t) stay here; the library gets their values and
+# derivatives at the knot times before each evaluation (integrators.jl:38-46, drives.jl:342-388).
+function upload_time_coefficients!(B::B200BilinearIntegrator, traj::NamedTrajectory)
+    isempty(B.modulations) && return
+    t = vec(traj[:t]); m = length(B.modulations)
+    c = [B.modulations[j][1](t[k]) for j in 1:m, k in 1:traj.N]                    # m × N, column-major
+    ċ = [B.modulations[j][2](t[k]) for j in 1:m, k in 1:traj.N]                    # ModulatedDrive.modulation_deriv
+    check(ccall((:pb2_set_time_coefficients, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint),
+                B.handle, c, ċ, PB2_HOST))
 end
 
 # ---- generator factors: exactly what the reference's closures add up per knot --------------------
@@ -72,7 +96,7 @@ end
 # closure built at quantum_systems.jl:212-227.
 generator_parts(sys::QuantumSystem) = (
     Matrix{Float64}(Piccolo.Isomorphisms.G(sys.H_drift)),
-    [Matrix{Float64}(Piccolo.Isomorphisms.G(Piccolo.drive_matrix(d))) for d in sys.H_drives],
+    [Matrix{Float64}(Piccolo.Isomorphisms.G(Piccolo.drive_matrix(base_drive(d)))) for d in sys.H_drives],
 )
 # Compact Lindbladian: the reference's integrator (integrators.jl:82-95) adds Σ_j rate_j 𝒢c_dissipators[j] to
 # the Hamiltonian drift through compact_generator_closure (open_quantum_systems.jl:607-636).  For
@@ -86,6 +110,16 @@ end
 # what the C ABI can express: coefficients u[index] (LinearDrive, drives.jl:52-55) and constant dissipation
 # rates (LinearDissipator, dissipators.jl:33-39); anything else keeps the reference's integrator
 linear_drives_only(sys) = all(d -> d isa Piccolo.LinearDrive, sys.H_drives)
+# ... and carrier-modulated linear drives, ModulatedDrive(LinearDrive(H_j, j), c_j) (drives.jl:342-388): the
+# generator stays separable, Ĝ(u, t) = G₀ + Σ_j c_j(t) u_j G_j, which the time-dependent handles evaluate
+separable_drive(d) = d isa Piccolo.LinearDrive || (d isa Piccolo.ModulatedDrive && d.base isa Piccolo.LinearDrive)
+separable_drives_only(sys::QuantumSystem) = all(separable_drive, sys.H_drives)
+base_drive(d) = d isa Piccolo.ModulatedDrive ? d.base : d
+# (c_j, ċ_j) per drive; the identity for unmodulated ones.  Empty when nothing is modulated.
+function drive_modulations(sys::QuantumSystem)
+    any(d -> d isa Piccolo.ModulatedDrive, sys.H_drives) || return Any[]
+    return Any[d isa Piccolo.ModulatedDrive ? (d.modulation, d.modulation_deriv) : (t -> 1.0, t -> 0.0) for d in sys.H_drives]
+end
 linear_drives_only(sys::OpenQuantumSystem) =
     all(d -> d isa Piccolo.LinearDrive, sys.H_drives) &&
     !Piccolo.has_nonlinear_dissipators(getfield(sys, :dissipators))
@@ -95,15 +129,17 @@ linear_drives_only(sys::OpenQuantumSystem) =
 # reference's own integrator, decided here at construction time.
 function Piccolo.BilinearIntegrator(qtraj::UnitaryTrajectory, traj::NamedTrajectory, ::Val{:b200})
     sys = qtraj.system
-    (sys.time_dependent || !linear_drives_only(sys)) && return BilinearIntegrator(qtraj, traj.N)
+    separable_drives_only(sys) || return BilinearIntegrator(qtraj, traj.N)
     G0, Gj = generator_parts(sys)
-    B200BilinearIntegrator(PB2_UNITARY, G0, Gj, traj, Piccolo.state_name(qtraj), Piccolo.drive_name(qtraj))
+    B200BilinearIntegrator(PB2_UNITARY, G0, Gj, traj, Piccolo.state_name(qtraj), Piccolo.drive_name(qtraj);
+                           modulations = drive_modulations(sys))
 end
 function Piccolo.BilinearIntegrator(qtraj::KetTrajectory, traj::NamedTrajectory, ::Val{:b200})
     sys = qtraj.system
-    (sys.time_dependent || !linear_drives_only(sys)) && return BilinearIntegrator(qtraj, traj.N)
+    separable_drives_only(sys) || return BilinearIntegrator(qtraj, traj.N)
     G0, Gj = generator_parts(sys)
-    B200BilinearIntegrator(PB2_KET, G0, Gj, traj, Piccolo.state_name(qtraj), Piccolo.drive_name(qtraj))
+    B200BilinearIntegrator(PB2_KET, G0, Gj, traj, Piccolo.state_name(qtraj), Piccolo.drive_name(qtraj);
+                           modulations = drive_modulations(sys))
 end
 function Piccolo.BilinearIntegrator(qtraj::DensityTrajectory, traj::NamedTrajectory, ::Val{:b200})
     sys = qtraj.system
@@ -139,8 +175,48 @@ function Piccolo.BilinearIntegrator(qtraj::SamplingTrajectory, traj::NamedTrajec
     return out
 end
 
+# All member integrators of an ensemble in ONE launch (pb2_batch_*): same constructor shape as above, one object.
+mutable struct B200IntegratorBatch
+    handle::Ptr{Cvoid}
+    names::Vector{Symbol}
+    dim::Int; nnz_jac::Int; nnz_hess::Int        # per member
+end
+function B200IntegratorBatch(kind, gens::Vector, traj::NamedTrajectory, names::Vector{Symbol}, u_name::Symbol; device = 0)
+    comps = traj.components
+    keep = Any[]
+    descs = map(zip(gens, names)) do ((G0, Gj), nm)
+        Gjflat = isempty(Gj) ? zeros(1) : reduce(vcat, vec.(Gj)); push!(keep, G0, Gjflat)
+        b = size(G0, 1)
+        PB2Desc(kind, b, kind == PB2_UNITARY ? b ÷ 2 : 1, length(Gj), traj.N, traj.dim, first(comps[nm]) - 1,
+                first(comps[traj.timestep]) - 1, first(comps[u_name]) - 1, traj.global_dim, 0, device, 0,
+                pointer(G0), pointer(Gjflat), 0, 0, 0)
+    end
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:pb2_batch_create, LIB), Cint, (Ptr{PB2Desc}, Cint, Ref{Ptr{Cvoid}}), descs, length(descs), h))
+    B = B200IntegratorBatch(h[], names, ccall((:pb2_batch_dim, LIB), Int64, (Ptr{Cvoid},), h[]),
+                            ccall((:pb2_batch_nnz_jac, LIB), Int64, (Ptr{Cvoid},), h[]),
+                            ccall((:pb2_batch_nnz_hess, LIB), Int64, (Ptr{Cvoid},), h[]))
+    finalizer(B -> ccall((:pb2_batch_destroy, LIB), Cvoid, (Ptr{Cvoid},), B.handle), B)
+    return B
+end
+"δ (dim × members) and Jacobian values (nnz_jac × members), member i = what member i's own integrator returns"
+function residual_jacobian!(δ::Matrix{Float64}, vals::Matrix{Float64}, B::B200IntegratorBatch, traj::NamedTrajectory)
+    check(ccall((:pb2_batch_residual_jacobian, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                B.handle, traj.datavec, δ, vals, PB2_HOST))
+end
+
+# rollout!(qtraj, pulse) for the trajectory's own zero-order-hold controls + rollout_divergence
+# (rollouts_extensions.jl:46-92, problems.jl:186-208, 336-356): states x_dim × N, out = (ε, ‖Δx_N‖, ‖x_N‖)
+function rollout(B::B200BilinearIntegrator, traj::NamedTrajectory; x0 = nothing)
+    states = Matrix{Float64}(undef, B.x_dim, traj.N); out = zeros(3)
+    check(ccall((:pb2_rollout, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint),
+                B.handle, traj.datavec, x0 === nothing ? C_NULL : x0, states, out, PB2_HOST))
+    return states, out[1]
+end
+
 # ---- the AbstractIntegrator interface --------------------------------------------------------------
 function DirectTrajOpt.evaluate!(δ::AbstractVector{Float64}, B::B200BilinearIntegrator, traj::NamedTrajectory)
+    upload_time_coefficients!(B, traj)
     check(ccall((:pb2_residual, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint),
                 B.handle, traj.datavec, δ, PB2_HOST))
     return nothing
@@ -153,6 +229,7 @@ function DirectTrajOpt.jacobian_structure(B::B200BilinearIntegrator)
 end
 
 function DirectTrajOpt.jacobian!(vals::AbstractVector{Float64}, B::B200BilinearIntegrator, traj::NamedTrajectory)
+    upload_time_coefficients!(B, traj)
     check(ccall((:pb2_jacobian, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Cint),
                 B.handle, traj.datavec, vals, PB2_HOST))
     return nothing
@@ -413,6 +490,19 @@ function DirectTrajOpt.gradient!(∇::AbstractVector{Float64}, J::B200Objective,
     fill!(view(∇, (J.layout[1]*J.layout[2]+1):length(∇)), 0.0)          # global variables: no dependence
     check(ccall((:pb2_obj_value_gradient, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}, Cint),
                 handle!(J), traj.datavec, v, ∇, PB2_HOST))
+    return nothing
+end
+
+# objective block of eval_h: σ ∇²J as COO (upper triangle, duplicates sum) -- pb2_obj_hessian
+function DirectTrajOpt.hessian_structure(J::B200Objective)
+    n = ccall((:pb2_obj_nnz_hess, LIB), Int64, (Ptr{Cvoid},), handle!(J))
+    rows = Vector{Int64}(undef, n); cols = similar(rows)
+    check(ccall((:pb2_obj_structure_hess, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), J.handle, rows, cols))
+    return collect(zip(rows, cols))
+end
+function hessian_values!(vals::AbstractVector{Float64}, J::B200Objective, traj::NamedTrajectory, σ::Float64)
+    check(ccall((:pb2_obj_hessian, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cdouble, Ptr{Float64}, Cint),
+                handle!(J), traj.datavec, σ, vals, PB2_HOST))
     return nothing
 end
 

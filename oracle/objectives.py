@@ -164,3 +164,34 @@ def quadratic_regularizer(V, dt, R, baseline=None, dt_power=0):
         return float(np.sum(q)), R[:, None] * dV, np.zeros_like(dt)
     return (float(np.sum(q * dt ** dt_power)), R[:, None] * dV * dt ** dt_power,
             q * dt_power * dt ** (dt_power - 1))
+
+
+# ------------------------------------------------------------------ second derivatives
+def hessian_from_gradient(grad_fn, x):
+    """Hessian of a loss  Q*|1 - F(x)|  or  Q*F(x)  with F at most quadratic in x (every term above):
+    away from the kink the gradient g(x) is affine in x, so column j of the Hessian is EXACTLY
+    (g(x + h e_j) - g(x - h e_j)) / 2h for any h that keeps 1 - F on the same side; h is taken small and
+    a power of two so that the difference quotient carries only rounding error.  ``grad_fn(x)`` returns
+    the gradient (the functions above, closed over their goal).  This is the complex-form statement the
+    kernel's real outer-product form (2 c scale (a_re a_re' + a_im a_im' + diag a_sq)) is checked against."""
+    x = np.asarray(x, dtype=float)
+    n, h = x.size, 2.0 ** -12
+    H = np.empty((n, n))
+    for j in range(n):
+        e = np.zeros(n)
+        e[j] = h
+        H[:, j] = (grad_fn(x + e) - grad_fn(x - e)) / (2 * h)
+    return 0.5 * (H + H.T)
+
+
+def quadratic_regularizer_hessian(V, dt, R, baseline=None, dt_power=0):
+    """PARITY UNPINNED like quadratic_regularizer.  Returns (d2J/dV2 diagonal [dim x T],
+    d2J/dV ddt [dim x T], d2J/ddt2 [T]) -- the regularizer couples a knot's rows only with that knot's dt."""
+    R = np.broadcast_to(np.asarray(R, dtype=float), (V.shape[0],))
+    dV = V if baseline is None else V - baseline
+    q = 0.5 * np.sum(R[:, None] * dV * dV, axis=0)
+    p = dt_power
+    if p == 0:
+        return np.broadcast_to(R[:, None], V.shape).copy(), np.zeros_like(V), np.zeros_like(dt)
+    return (R[:, None] * dt ** p * np.ones_like(V), R[:, None] * dV * p * dt ** (p - 1),
+            q * p * (p - 1) * (dt ** (p - 2) if p > 1 else 0.0))

@@ -23,7 +23,7 @@ from .generators import (  # noqa: F401
     density_lift_matrix, density_projection_matrix,
 )
 from .integrators import (  # noqa: F401
-    B200BilinearIntegrator, B200KnotLinearConstraints, BilinearIntegrator, DensityTrajectory, KetTrajectory,
+    B200BilinearIntegrator, B200IntegratorBatch, B200KnotLinearConstraints, BilinearIntegrator, DensityTrajectory, KetTrajectory,
     MultiDensityTrajectory, MultiKetTrajectory, NamedTrajectory, OpenQuantumSystem, QuantumSystem, SamplingTrajectory, UnitaryTrajectory,
     eval_jacobian, evaluate_, hessian_of_lagrangian, hessian_structure, jacobian_structure, rollout_divergence,
     test_integrator,

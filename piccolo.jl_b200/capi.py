@@ -25,8 +25,14 @@ SYMBOLS = [
     "pb2_aux_structure_jac", "pb2_aux_structure_hess", "pb2_aux_residual_jacobian", "pb2_aux_hess_lagrangian",
     "pb2_aux_residual_jacobian_async",
     "pb2_obj_create", "pb2_obj_destroy", "pb2_obj_value_gradient", "pb2_obj_value_gradient_async",
+    "pb2_obj_nnz_hess", "pb2_obj_structure_hess", "pb2_obj_hessian", "pb2_obj_hessian_async",
     "pb2_stream", "pb2_sync", "pb2_set_option", "pb2_rollout", "pb2_rollout_async",
     "pb2_set_time_coefficients", "pb2_host_alloc", "pb2_host_free", "pb2_launch_count",
+    "pb2_device_alloc", "pb2_device_free", "pb2_device_copy", "pb2_ipc_export", "pb2_ipc_open", "pb2_ipc_close",
+    "pb2_batch_create", "pb2_batch_destroy", "pb2_batch_size", "pb2_batch_fused", "pb2_batch_dim",
+    "pb2_batch_nnz_jac", "pb2_batch_nnz_hess", "pb2_batch_structure_jac", "pb2_batch_structure_hess",
+    "pb2_batch_residual_jacobian", "pb2_batch_hess_lagrangian", "pb2_batch_residual_jacobian_async",
+    "pb2_batch_hess_lagrangian_async",
 ]
 
 
@@ -44,6 +50,7 @@ class pb2_desc(ctypes.Structure):
         ("global_dim", ctypes.c_int32), ("knot0", ctypes.c_int64), ("device", ctypes.c_int32),
         ("algorithm", ctypes.c_int32), ("G0", ctypes.POINTER(ctypes.c_double)),
         ("Gj", ctypes.POINTER(ctypes.c_double)), ("t_off", ctypes.c_int32), ("time_dependent", ctypes.c_int32),
+        ("dense_blocks", ctypes.c_int32),
     ]
 
 
@@ -132,6 +139,27 @@ def load_library():
     L.pb2_residual_jacobian_exchange_async.argtypes = [H, vp, ctypes.c_int32, ctypes.c_int32,
                                                        ctypes.POINTER(vp), ctypes.c_int64, vp]
     L.pb2_set_option.argtypes = [H, ctypes.c_int32, ctypes.c_int64]
+    L.pb2_device_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_int64, ctypes.c_int32]
+    L.pb2_device_free.argtypes = [vp]
+    L.pb2_device_copy.argtypes = [vp, vp, ctypes.c_int64]
+    L.pb2_ipc_export.argtypes = [vp, vp]
+    L.pb2_ipc_open.argtypes = [vp, ctypes.c_int32, ctypes.POINTER(vp)]
+    L.pb2_ipc_close.argtypes = [vp]
+    L.pb2_batch_create.argtypes = [ctypes.POINTER(pb2_desc), ctypes.c_int32, ctypes.POINTER(H)]
+    L.pb2_batch_destroy.argtypes = [H]
+    L.pb2_batch_destroy.restype = None
+    for f in ("pb2_batch_size", "pb2_batch_fused"):
+        getattr(L, f).argtypes = [H]
+        getattr(L, f).restype = ctypes.c_int32
+    for f in ("pb2_batch_dim", "pb2_batch_nnz_jac", "pb2_batch_nnz_hess"):
+        getattr(L, f).argtypes = [H]
+        getattr(L, f).restype = ctypes.c_int64
+    L.pb2_batch_structure_jac.argtypes = [H, ctypes.c_int32, ip, ip]
+    L.pb2_batch_structure_hess.argtypes = [H, ctypes.c_int32, ip, ip]
+    L.pb2_batch_residual_jacobian.argtypes = [H, vp, vp, vp, ctypes.c_int]
+    L.pb2_batch_hess_lagrangian.argtypes = [H, vp, vp, vp, ctypes.c_int]
+    L.pb2_batch_residual_jacobian_async.argtypes = [H, vp, vp, vp, vp]
+    L.pb2_batch_hess_lagrangian_async.argtypes = [H, vp, vp, vp, vp]
     L.pb2_set_time_coefficients.argtypes = [H, vp, vp, ctypes.c_int]
     L.pb2_rollout.argtypes = [H, vp, vp, vp, vp, ctypes.c_int]
     L.pb2_rollout_async.argtypes = [H, vp, vp, vp, vp, vp]
@@ -155,6 +183,11 @@ def load_library():
     L.pb2_obj_destroy.restype = None
     L.pb2_obj_value_gradient.argtypes = [H, vp, vp, vp, ctypes.c_int]
     L.pb2_obj_value_gradient_async.argtypes = [H, vp, vp, vp, vp]
+    L.pb2_obj_nnz_hess.argtypes = [H]
+    L.pb2_obj_nnz_hess.restype = ctypes.c_int64
+    L.pb2_obj_structure_hess.argtypes = [H, ip, ip]
+    L.pb2_obj_hessian.argtypes = [H, vp, ctypes.c_double, vp, ctypes.c_int]
+    L.pb2_obj_hessian_async.argtypes = [H, vp, ctypes.c_double, vp, vp]
     L.pb2_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_int64]
     L.pb2_host_free.argtypes = [vp]
     _lib = L

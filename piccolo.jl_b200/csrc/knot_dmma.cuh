@@ -72,12 +72,22 @@ struct DmmaParams {
   double* delta;
   double* jac;
   long long* trace;      // debug: per-phase clock64 stamps of block 0 (null in production)
+  // batched launch (pb2_batch_*, blockIdx.y = member of a SamplingTrajectory ensemble): own tables and state block
+  // per member, one shared trajectory
+  int mem_n;                                   // 0 / 1: not batched
+  const int* x_offs;                           // [mem_n]
+  long long mem_gfrag, mem_ell, mem_norms;     // strides (elements) between the members' tables
+  long long mem_delta, mem_jac;                // strides (doubles) between the members' outputs
 };
 
 constexpr int kDmmaMaxTiles = 8;
 constexpr int kDmmaMaxW = 4;
 constexpr int kDmmaMaxGroups = 7;     // 2 named barriers per group, ids 1..14
 constexpr int kDmmaMaxThreads = 512;
+// Threads per CTA by generator size: the 16 x 16 variants (e.g. the compact
+// Lindbladians, BASELINE config C4) keep 2 x 4 x W coupling values and addresses per lane next to 8 generator fragments; at 512 threads
+// (128 registers) they spilled 0.5 - 1 KB per thread into the Horner loop, at 256 threads they fit.
+__host__ __device__ constexpr int dmma_max_threads(int NT, int W) { return NT == 2 ? 256 : kDmmaMaxThreads; }
 
 // c_invfact[k] = 1 / k!
 __constant__ double c_invfact[kMaxDeg + 1];
@@ -227,9 +237,16 @@ __device__ __forceinline__ void horner_run(int M, double (&t)[2 * NT], const dou
 
 // NT = padded generator size / 8 (1 or 2); W = ELL width of the drive generators (1, 2 or 4).
 template <int NT, int W>
-__global__ void __launch_bounds__(kDmmaMaxThreads, 1) knot_dmma_kernel(const __grid_constant__ DmmaParams p) {
+__global__ void __launch_bounds__(dmma_max_threads(NT, W), 1) knot_dmma_kernel(DmmaParams p) {
   constexpr int KT = 2 * NT, Bp = 8 * NT, FR = KT * NT * 32;
   extern __shared__ __align__(16) double dmma_smem[];
+  if (p.mem_n > 1) {
+    const long long mi = blockIdx.y;
+    p.Gfrag += mi * p.mem_gfrag;
+    p.ell += mi * p.mem_ell;
+    p.norms += mi * p.mem_norms;
+  }
+  apply_member(p);
   const int lane = threadIdx.x & 31, wcta = threadIdx.x >> 5;
   const int tiles = p.tiles;
   const int group = wcta / tiles, w = wcta - group * tiles;

@@ -23,7 +23,24 @@ struct KnotParams {
   double* jac;        // device or null
   const double* mu;   // device (hessian only)
   double* hess;       // device (hessian only)
+  // batched launch (pb2_batch_*: the members of a SamplingTrajectory ensemble, blockIdx.y = member): every member
+  // has its own generator factors and state block, all read the same trajectory
+  int mem_n;                    // 0 / 1: not batched
+  const int* x_offs;            // [mem_n] state-block row of each member
+  long long mem_G0, mem_Gj;     // strides (doubles) between the members' generator factors
+  long long mem_delta, mem_jac, mem_hess;   // strides between the members' outputs (mem_delta also strides mu)
 };
+
+// batched launches: shift the member-dependent fields of a by-value parameter block
+template <class P>
+__device__ __forceinline__ void apply_member(P& p) {
+  if (p.mem_n > 1) {
+    const long long mi = blockIdx.y;
+    p.x_off = p.x_offs[mi];
+    if (p.delta) p.delta += mi * p.mem_delta;
+    if (p.jac) p.jac += mi * p.mem_jac;
+  }
+}
 
 constexpr int kMaxDeg = 18;
 // c_theta[q]: largest ||A||_1 for which the degree-q Taylor polynomial of exp is accurate
@@ -63,6 +80,14 @@ __global__ void __launch_bounds__(NT) knot_generic_kernel(KnotParams p, int GS, 
   extern __shared__ double sm[];
   __shared__ int s_M, s_s;
 
+  if (p.mem_n > 1) {
+    const long long mi = blockIdx.y;
+    p.G0 += mi * p.mem_G0;
+    p.Gj += mi * p.mem_Gj;
+    if (p.mu) p.mu += mi * p.mem_delta;
+    if (p.hess) p.hess += mi * p.mem_hess;
+  }
+  apply_member(p);
   const int b = p.b, bb = b * b, n_b = p.n_b, n_x = b * n_b, m = p.m;
   const int npair = (ORDER == 2) ? m * (m + 1) / 2 : 0;
   const int S = 1 + m + npair;                 // jet slabs

@@ -43,6 +43,11 @@ struct ObjParams {
   double* J;                // 1
   double* Jpart;            // K
   unsigned int* counter;
+  // Hessian (knot_objective_hess_kernel)
+  const int* t_kind;        // per term: 0 = no second derivative (a_lin only), 1 = diagonal (a_sq only), 2 = dense block
+  const long long* hess_ptr;   // K+1: first Hessian entry of each knot
+  double* hess;
+  double sigma;             // Ipopt's obj_factor
 };
 
 constexpr int kObjThreads = 128;
@@ -173,6 +178,88 @@ __global__ void __launch_bounds__(kObjThreads) knot_objective_kernel(ObjParams p
   if (tid == 0) {
     *p.J = s1[0];
     *p.counter = 0u;
+  }
+}
+
+// Hessian of sigma * J over the trajectory entries, upper triangle, COO values in the order pb2_obj_structure_hess
+// lists them: knot-major; inside a knot first the term instances (a dense term: the upper triangle of its
+// n_rows x n_rows block, column-major; an a_sq-only term: its diagonal; an a_lin-only term: nothing), then the
+// active regularizers (n_rows diagonal entries, and for dt_power > 0 n_rows (z_i, dt) entries and one (dt, dt)).
+//   loss = Q |1 - F| :  d2 loss = c d2F,  c = -Q sign(1 - F)   (almost everywhere; ForwardDiff's convention at 0)
+//   d2F[i,j] = 2 scale (a_re_i a_re_j + a_im_i a_im_j + [i == j] a_sq_i)
+//   reg = 1/2 sum_i R_i dv_i^2 dt^p :  (z_i,z_i) R_i dt^p;  (z_i,dt) R_i dv_i p dt^(p-1);  (dt,dt) 1/2 q p (p-1) dt^(p-2)
+// Same one-CTA-per-knot shape as the gradient kernel; the only large block is the terminal one.
+__global__ void __launch_bounds__(kObjThreads) knot_objective_hess_kernel(ObjParams p) {
+  extern __shared__ double smem_obj[];
+  double* z = smem_obj;
+  __shared__ double red[4 * (kObjThreads / 32)];
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const double* Zk = p.Z + (size_t)k * p.D;
+  for (int i = tid; i < p.D; i += kObjThreads) z[i] = Zk[i];
+  __syncthreads();
+  long long o = p.hess_ptr[k];
+  if (o == p.hess_ptr[k + 1]) return;
+  for (int it = p.knot_ptr[k]; it < p.knot_ptr[k + 1]; ++it) {
+    const int t = p.item_term[it], kind = p.t_kind[t];
+    if (kind == 0) continue;
+    const double Q = p.item_q[it];
+    const int o0 = p.t_off[t], n = p.t_off[t + 1] - o0;
+    const double sc = p.t_scale[t];
+    double c = Q;
+    if (p.t_flags[t] & 1) {
+      double s[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int i = tid; i < n; i += kObjThreads) {
+        const double zi = z[p.rows[o0 + i]];
+        s[0] = fma(p.a_re[o0 + i], zi, s[0]);
+        s[1] = fma(p.a_im[o0 + i], zi, s[1]);
+        s[2] = fma(p.a_sq[o0 + i] * zi, zi, s[2]);
+        s[3] = fma(p.a_lin[o0 + i], zi, s[3]);
+      }
+      obj_block_sum(s, red);
+      const double F = sc * (s[0] * s[0] + s[1] * s[1] + s[2]) + s[3];
+      c = signbit(1.0 - F) ? Q : -Q;
+    }
+    const double w = 2.0 * p.sigma * c * sc;
+    if (kind == 1) {
+      for (int i = tid; i < n; i += kObjThreads) p.hess[o + i] = w * p.a_sq[o0 + i];
+      o += n;
+    } else {
+      const long long ne = (long long)n * (n + 1) / 2;
+      for (long long e = tid; e < ne; e += kObjThreads) {
+        int j = (int)((sqrt(8.0 * (double)e + 1.0) - 1.0) * 0.5);
+        while ((long long)(j + 1) * (j + 2) / 2 <= e) ++j;
+        while ((long long)j * (j + 1) / 2 > e) --j;
+        const int i = (int)(e - (long long)j * (j + 1) / 2);
+        double v = p.a_re[o0 + i] * p.a_re[o0 + j] + p.a_im[o0 + i] * p.a_im[o0 + j];
+        if (i == j) v += p.a_sq[o0 + i];
+        p.hess[o + e] = w * v;
+      }
+      o += ne;
+    }
+  }
+  const double dt = z[p.dt_off];
+  for (int r = 0; r < p.n_regs; ++r) {
+    if (p.r_w[(size_t)r * p.K + k] == 0.0) continue;
+    const int o0 = p.r_off[r], n = p.r_off[r + 1] - o0, pw = p.r_pow[r];
+    const double dtp = pw == 0 ? 1.0 : (pw == 1 ? dt : dt * dt);
+    const double ddtp = pw == 0 ? 0.0 : (pw == 1 ? 1.0 : 2.0 * dt);
+    const double* base = p.r_base[r];
+    double q[1] = {0.0};
+    for (int i = tid; i < n; i += kObjThreads) {
+      const int row = p.r_rows[o0 + i];
+      const double dv = base ? z[row] - base[(size_t)k * n + i] : z[row];
+      const double Rd = p.r_R[o0 + i] * dv;
+      q[0] = fma(Rd, dv, q[0]);
+      p.hess[o + i] = p.sigma * p.r_R[o0 + i] * dtp;
+      // a regularised timestep row meets itself in the cross term: both orders land on (dt, dt)
+      if (pw) p.hess[o + n + i] = p.sigma * Rd * ddtp * (row == p.dt_off ? 2.0 : 1.0);
+    }
+    o += n;
+    if (pw) {
+      obj_block_sum(q, red);
+      if (tid == 0) p.hess[o + n] = pw == 2 ? p.sigma * q[0] : 0.0;
+      o += n + 1;
+    }
   }
 }
 

@@ -117,8 +117,34 @@ double theta_bound(int q) {
 
 }  // namespace
 
+// dense_blocks: canonical values [n_b x (b x b) | rest] -> [n_x x n_x dense block, zeros included | rest]; one CTA
+// per knot (grid-stride).  Pure data movement (HBM-bound).
+__global__ void __launch_bounds__(256) dense_blocks_kernel(const double* __restrict__ canon, double* __restrict__ out,
+                                                           long long n_knots, int b, int n_b, int nnz_canon, int nnz_dense) {
+  const int n_x = b * n_b, bb = b * b, rest = nnz_canon - n_b * bb;
+  for (long long k = blockIdx.x; k < n_knots; k += gridDim.x) {
+    const double* src = canon + k * nnz_canon;
+    double* dst = out + k * nnz_dense;
+    for (int e = threadIdx.x; e < n_x * n_x; e += blockDim.x) {
+      const int col = e / n_x, row = e - col * n_x, cb = col / b, rb = row / b;
+      dst[e] = cb == rb ? src[cb * bb + (col - cb * b) * b + (row - rb * b)] : 0.0;
+    }
+    for (int e = threadIdx.x; e < rest; e += blockDim.x) dst[n_x * n_x + e] = src[n_b * bb + e];
+  }
+}
+
+// One launch for all members of an ensemble (pb2_batch_*): member-dependent arrays and strides (blockIdx.y = member)
+struct BatchLaunch {
+  int n = 0, max_xoff = 0;
+  const int* x_offs = nullptr;
+  const double *G0 = nullptr, *Gj = nullptr, *gfrag = nullptr, *norms = nullptr;
+  const pb2::EllEntry* ell = nullptr;
+  long long mem_G0 = 0, mem_Gj = 0, mem_gfrag = 0, mem_ell = 0, mem_norms = 0, mem_delta = 0, mem_jac = 0, mem_hess = 0;
+};
+
 struct pb2_handle {
   pb2_desc d{};
+  const BatchLaunch* batch = nullptr;   // set around a batched launch on the ensemble's first member
   std::vector<double> G0, Gj;
   int alg = PB2_ALG_GENERIC;
   cudaStream_t stream = nullptr;
@@ -167,7 +193,10 @@ struct pb2_handle {
 
   int n_x() const { return d.b * d.n_b; }
   int64_t nk() const { return (int64_t)d.K - 1; }
+  // canonical values per knot (what the kernels write) and what the caller sees (dense_blocks: full n_x x n_x block)
   int nnz_jac_knot() const { return d.n_b * d.b * d.b + n_x() * d.m + 2 * n_x() + (d.time_dependent ? n_x() : 0); }
+  int nnz_jac_user_knot() const { return d.dense_blocks ? nnz_jac_knot() - d.n_b * d.b * d.b + n_x() * n_x() : nnz_jac_knot(); }
+  double* dCanon = nullptr;    // dense_blocks: the kernels' canonical values before re-layout
   int nnz_hess_knot() const { return n_x() * d.m + n_x() + d.m * (d.m + 1) / 2 + d.m + 1; }
 };
 
@@ -185,10 +214,30 @@ pb2::KnotParams make_params(const pb2_handle* h) {
 int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, int compact,
                        int n_peers, double* const* peers, int self, int z_stable);
 
-// Every residual / Jacobian launch goes through here.  Time-dependent handles: scale the drive rows by c_j(t_k),
-// run the knot kernels on the scaled copy, then apply the chain rule to the finished values (knot_td.cuh).
+int launch_resjac_td(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, int compact,
+                     int n_peers, double* const* peers, int self, int z_stable);
+
+// Every residual / Jacobian launch of the entry points goes through here.  dense_blocks handles: the kernels write
+// their canonical values into the handle's scratch, one streaming pass re-lays them out for the caller.
 int launch_resjac(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, int compact = 0,
                   int n_peers = 0, double* const* peers = nullptr, int self = 0, int z_stable = 0) {
+  if (!h->d.dense_blocks || !djac) return launch_resjac_td(h, dZ, ddelta, djac, st, compact, n_peers, peers, self, z_stable);
+  if (h->nk() <= 0) return PB2_OK;
+  if (compact || n_peers) return fail(PB2_EINVAL, "dense_blocks handles do not produce compact records");
+  if (!h->dCanon) PB2_CUDA(cudaMalloc(&h->dCanon, (size_t)h->nnz_jac_knot() * h->nk() * sizeof(double)));
+  int rc = launch_resjac_td(h, dZ, ddelta, h->dCanon, st, 0, 0, nullptr, 0, z_stable);
+  if (rc) return rc;
+  dense_blocks_kernel<<<(unsigned)std::min<int64_t>(h->nk(), 148 * 8), 256, 0, st>>>(
+      h->dCanon, djac, h->nk(), h->d.b, h->d.n_b, h->nnz_jac_knot(), h->nnz_jac_user_knot());
+  PB2_CUDA(cudaGetLastError());
+  h->launches++;
+  return PB2_OK;
+}
+
+// Time-dependent handles: scale the drive rows by c_j(t_k), run the knot kernels on the scaled copy, then apply the
+// chain rule to the finished values (knot_td.cuh).
+int launch_resjac_td(pb2_handle* h, const double* dZ, double* ddelta, double* djac, cudaStream_t st, int compact,
+                     int n_peers, double* const* peers, int self, int z_stable) {
   if (!h->d.time_dependent) return launch_resjac_core(h, dZ, ddelta, djac, st, compact, n_peers, peers, self, z_stable);
   if (h->nk() <= 0) return PB2_OK;
   if (compact || n_peers) return fail(PB2_EINVAL, "time-dependent handles do not produce compact records");
@@ -216,7 +265,12 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
   if (h->nk() <= 0) return PB2_OK;
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.delta = ddelta; p.jac = djac;
-  const bool aligned16 = ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0);
+  const BatchLaunch* bl = h->batch;
+  const bool aligned16 = !bl && ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0);
+  if (bl) {
+    p.mem_n = bl->n; p.x_offs = bl->x_offs; p.G0 = bl->G0; p.Gj = bl->Gj;
+    p.mem_G0 = bl->mem_G0; p.mem_Gj = bl->mem_Gj; p.mem_delta = bl->mem_delta; p.mem_jac = bl->mem_jac;
+  }
   if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8q && !h->u8s && djac && aligned16 && (p.D % 2 == 0) &&
       (p.x_off % 2 == 0) && (n_peers == 0 || !std::getenv("PB2_U8Q_NO_PEERS")) &&
       (h->u8q >= 2 || h->nk() <= (int64_t)7 * h->n_sm)) {
@@ -397,23 +451,34 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
     q.Gfrag = h->dGfrag; q.ell = h->dEll; q.norms = h->dNorms;
     q.Z = dZ; q.delta = ddelta; q.jac = djac; q.trace = h->dTrace;
     const int bb = p.b * p.b, n_x = p.b * p.n_b;
+    if (bl) {
+      // all members of the ensemble in this launch: own tables and state block per member (blockIdx.y)
+      q.mem_n = bl->n; q.x_offs = bl->x_offs; q.Gfrag = bl->gfrag; q.ell = bl->ell; q.norms = bl->norms;
+      q.mem_gfrag = bl->mem_gfrag; q.mem_ell = bl->mem_ell; q.mem_norms = bl->mem_norms;
+      q.mem_delta = bl->mem_delta; q.mem_jac = bl->mem_jac;
+      q.zlen = p.D + bl->max_xoff + n_x;        // the slab covers the furthest member's next-knot state
+    }
     q.bulk_in = (p.D % 2 == 0) && (q.zlen % 2 == 0) && ((uintptr_t)dZ % 16 == 0);
-    q.bulk_out = (bb % 2 == 0) && (n_x % 2 == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0);
+    q.bulk_out = (bb % 2 == 0) && (n_x % 2 == 0) && ((uintptr_t)ddelta % 16 == 0) && ((uintptr_t)djac % 16 == 0) &&
+                 (!bl || (bl->mem_delta % 2 == 0 && bl->mem_jac % 2 == 0));
     // persistent grid: one CTA per SM, gpc knot groups per CTA (bounded by threads, barriers, smem)
-    int maxg = std::min(pb2::kDmmaMaxGroups, pb2::kDmmaMaxThreads / (32 * q.tiles));
+    int maxg = std::min(pb2::kDmmaMaxGroups, pb2::dmma_max_threads(pl.NT, pl.W) / (32 * q.tiles));
     while (maxg > 1 && pb2::dmma_layout(q, pl.NT, maxg) > kSmemLimit) --maxg;
-    const int per_sm = (q.nk + h->n_sm - 1) / h->n_sm;
-    q.gpc = std::max(1, std::min(maxg, h->gpc_override > 0 ? h->gpc_override : std::min(per_sm, h->gpc_default)));
-    const int blocks = std::min(h->n_sm, (q.nk + q.gpc - 1) / q.gpc);
+    // (an ensemble shares the SMs: one wave of persistent CTAs over all members, each CTA walking its member's knots
+    // with as many groups as fit -- a CTA per two knots would pay the prologue once per wave instead of once)
+    const int n_mem = bl ? bl->n : 1;
+    const int per_sm = (int)(((long long)q.nk * n_mem + h->n_sm - 1) / h->n_sm);
+    q.gpc = std::max(1, std::min(maxg, h->gpc_override > 0 ? h->gpc_override : std::min(per_sm, bl ? maxg : h->gpc_default)));
+    const int blocks = std::min(std::max(1, h->n_sm / n_mem), (q.nk + q.gpc - 1) / q.gpc);
     const size_t smem = pb2::dmma_layout(q, pl.NT, q.gpc);
     if (smem > kSmemLimit) return fail(PB2_EINVAL, "dmma resjac: knot column too large for the shared-memory staging");
-    pb2::dmma_kernel(pl.NT, pl.W)<<<blocks, 32 * q.tiles * q.gpc, smem, st>>>(q);
+    pb2::dmma_kernel(pl.NT, pl.W)<<<dim3(blocks, bl ? bl->n : 1), 32 * q.tiles * q.gpc, smem, st>>>(q);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("dmma resjac launch: ") + cudaGetErrorString(e));
   } else {
     const LaunchCfg& c = h->cfg1;
     const int blocks = (int)((h->nk() + c.KPC - 1) / c.KPC);
-    pb2::knot_generic_kernel<1, kNT><<<blocks, kNT, c.smem, st>>>(p, c.GS, c.KPC, c.gj_in_smem);
+    pb2::knot_generic_kernel<1, kNT><<<dim3(blocks, bl ? bl->n : 1), kNT, c.smem, st>>>(p, c.GS, c.KPC, c.gj_in_smem);
     PB2_CUDA(cudaGetLastError());
   }
   h->launches++;
@@ -427,7 +492,12 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
                             "integrator or a quasi-Newton Hessian)");
   pb2::KnotParams p = make_params(h);
   p.Z = dZ; p.mu = dmu; p.hess = dhess;
-  if (h->u8h_ok && ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)dmu % 16 == 0) && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
+  const BatchLaunch* bl = h->batch;
+  if (bl) {
+    p.mem_n = bl->n; p.x_offs = bl->x_offs; p.G0 = bl->G0; p.Gj = bl->Gj;
+    p.mem_G0 = bl->mem_G0; p.mem_Gj = bl->mem_Gj; p.mem_delta = bl->mem_delta; p.mem_hess = bl->mem_hess;
+  }
+  if (!bl && h->u8h_ok && ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)dmu % 16 == 0) && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
     // 3-qubit unitary shape, anti-symmetric generators: tensor-core Hessian (forward + adjoint jets)
     pb2::U8hParams q{};
     q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
@@ -449,7 +519,7 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
     // the Lagrangian Hessian always runs the jet kernel (second-order jets)
     const LaunchCfg& c = h->cfg2;
     const int blocks = (int)((h->nk() + c.KPC - 1) / c.KPC);
-    pb2::knot_generic_kernel<2, kNT><<<blocks, kNT, c.smem, st>>>(p, c.GS, c.KPC, c.gj_in_smem);
+    pb2::knot_generic_kernel<2, kNT><<<dim3(blocks, bl ? bl->n : 1), kNT, c.smem, st>>>(p, c.GS, c.KPC, c.gj_in_smem);
     PB2_CUDA(cudaGetLastError());
   }
   h->launches++;
@@ -742,6 +812,7 @@ void pb2_destroy(pb2_handle* h) {
   if (h->dTablesQ) cudaFree(h->dTablesQ);
   if (h->dSmClock) cudaFree(h->dSmClock);
   if (h->dSyncWords) cudaFree(h->dSyncWords);
+  if (h->dCanon) cudaFree(h->dCanon);
   for (double* q : {h->dCoef, h->dCoefDot, h->dZs})
     if (q) cudaFree(q);
   for (double* q : {h->dRoJac, h->dRoStates, h->dRoX0, h->dRoOut})
@@ -761,7 +832,7 @@ void pb2_destroy(pb2_handle* h) {
 }
 
 int64_t pb2_dim(const pb2_handle* h) { return h ? (int64_t)h->n_x() * h->nk() : -1; }
-int64_t pb2_nnz_jac(const pb2_handle* h) { return h ? (int64_t)h->nnz_jac_knot() * h->nk() : -1; }
+int64_t pb2_nnz_jac(const pb2_handle* h) { return h ? (int64_t)h->nnz_jac_user_knot() * h->nk() : -1; }
 int64_t pb2_nnz_hess(const pb2_handle* h) { return h ? (int64_t)h->nnz_hess_knot() * h->nk() : -1; }
 int32_t pb2_algorithm(const pb2_handle* h) { return h ? h->alg : -1; }
 int64_t pb2_launch_count(const pb2_handle* h) { return h ? h->launches : -1; }
@@ -796,6 +867,13 @@ int pb2_structure_jac(const pb2_handle* h, int64_t* rows, int64_t* cols) {
   for (int64_t kl = 0; kl < h->nk(); ++kl) {
     const int64_t k = d.knot0 + kl;
     const int64_t r0 = k * n_x + 1, c0 = k * D + 1;
+    if (d.dense_blocks) {
+      for (int64_t j = 0; j < n_x; ++j)
+        for (int64_t i = 0; i < n_x; ++i) {
+          rows[o] = r0 + i;
+          cols[o++] = c0 + d.x_off + j;
+        }
+    } else
     for (int64_t c = 0; c < n_b; ++c)
       for (int64_t j = 0; j < b; ++j)
         for (int64_t i = 0; i < b; ++i) {
@@ -864,7 +942,7 @@ int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu
 }
 
 int64_t pb2_compact_stride(const pb2_handle* h) {
-  if (!h || !(h->alg == PB2_ALG_DMMA && h->u8_ok) || (h->d.D % 2) || (h->d.x_off % 2) || h->d.time_dependent) return 0;
+  if (!h || !(h->alg == PB2_ALG_DMMA && h->u8_ok) || (h->d.D % 2) || (h->d.x_off % 2) || h->d.time_dependent || h->d.dense_blocks) return 0;
   return (int64_t)(h->d.m + 3) * 128;
 }
 
@@ -1103,13 +1181,231 @@ int pb2_set_time_coefficients(pb2_handle* h, const double* c, const double* cdot
   return PB2_OK;
 }
 
+static int aux_ensure(double** dev, size_t n) {
+  if (!*dev) PB2_CUDA(cudaMalloc(dev, std::max<size_t>(n, 1) * sizeof(double)));
+  return PB2_OK;
+}
+
+// ---- ensembles: all members in one launch ------------------------------------------------------------------
+struct pb2_batch {
+  std::vector<pb2_handle*> mem;
+  bool fused = false;
+  BatchLaunch bl;
+  int* dXoffs = nullptr;
+  double *dG0 = nullptr, *dGj = nullptr, *dGfrag = nullptr, *dNorms = nullptr;
+  pb2::EllEntry* dEll = nullptr;
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> done;
+  cudaEvent_t fork = nullptr;
+  double *dZ = nullptr, *dDelta = nullptr, *dJac = nullptr, *dMu = nullptr, *dHess = nullptr;
+};
+
+void pb2_batch_destroy(pb2_batch* b) {
+  if (!b) return;
+  if (!b->mem.empty()) {
+    DeviceGuard guard(b->mem[0]->d.device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (void* q : {(void*)b->dXoffs, (void*)b->dG0, (void*)b->dGj, (void*)b->dGfrag, (void*)b->dNorms, (void*)b->dEll,
+                    (void*)b->dZ, (void*)b->dDelta, (void*)b->dJac, (void*)b->dMu, (void*)b->dHess})
+      if (q) cudaFree(q);
+    for (cudaEvent_t e : b->done)
+      if (e) cudaEventDestroy(e);
+    if (b->fork) cudaEventDestroy(b->fork);
+    if (b->stream) cudaStreamDestroy(b->stream);
+  }
+  for (pb2_handle* h : b->mem) pb2_destroy(h);
+  delete b;
+}
+
+int pb2_batch_create(const pb2_desc* descs, int32_t n, pb2_batch** out) {
+  if (!descs || !out || n < 1) return fail(PB2_EINVAL, "pb2_batch_create: bad argument");
+  *out = nullptr;
+  const pb2_desc& d0 = descs[0];
+  for (int i = 1; i < n; ++i) {
+    const pb2_desc& d = descs[i];
+    if (d.kind != d0.kind || d.b != d0.b || d.n_b != d0.n_b || d.m != d0.m || d.K != d0.K || d.D != d0.D ||
+        d.dt_off != d0.dt_off || d.u_off != d0.u_off || d.global_dim != d0.global_dim || d.device != d0.device ||
+        d.algorithm != d0.algorithm || d.knot0 != d0.knot0)
+      return fail(PB2_EINVAL, "pb2_batch_create: members must agree in everything but x_off and the generators");
+  }
+  for (int i = 0; i < n; ++i)
+    if (descs[i].time_dependent || descs[i].dense_blocks)
+      return fail(PB2_EINVAL, "pb2_batch_create: time-dependent / dense_blocks members are not supported");
+  pb2_batch* b = new (std::nothrow) pb2_batch();
+  if (!b) return fail(PB2_ENOMEM, "pb2_batch_create: out of memory");
+  for (int i = 0; i < n; ++i) {
+    pb2_handle* h = nullptr;
+    const int rc = pb2_create(&descs[i], &h);
+    if (rc) {
+      const std::string msg = g_err;
+      pb2_batch_destroy(b);
+      return fail(rc, msg);
+    }
+    b->mem.push_back(h);
+  }
+  DeviceGuard guard(d0.device);
+  auto bail = [&](const char* what) {
+    pb2_batch_destroy(b);
+    return fail(PB2_ECUDA, std::string("pb2_batch_create: ") + what);
+  };
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+  if (cudaEventCreateWithFlags(&b->fork, cudaEventDisableTiming) != cudaSuccess) return bail("event");
+  b->done.assign(n, nullptr);
+  for (int i = 0; i < n; ++i)
+    if (cudaEventCreateWithFlags(&b->done[i], cudaEventDisableTiming) != cudaSuccess) return bail("event");
+  // can the members share one launch?  same algorithm, same tensor-core plan shape, not the 3-qubit kernels
+  const pb2_handle* h0 = b->mem[0];
+  bool same = true;
+  for (const pb2_handle* h : b->mem) {
+    same = same && h->alg == h0->alg && !h->u8_ok;
+    if (h->alg == PB2_ALG_DMMA)
+      same = same && h->plan.NT == h0->plan.NT && h->plan.W == h0->plan.W && h->plan.iso == h0->plan.iso &&
+             h->plan.ncT == h0->plan.ncT && h->plan.tiles_full == h0->plan.tiles_full;
+  }
+  if (std::getenv("PB2_BATCH_NO_FUSE")) same = false;
+  b->fused = same && n > 1;
+  if (b->fused) {
+    const size_t bb = (size_t)d0.b * d0.b;
+    std::vector<int> xo(n);
+    std::vector<double> G0((size_t)n * bb), Gj((size_t)n * std::max<size_t>(1, (size_t)d0.m * bb));
+    int mx = 0;
+    for (int i = 0; i < n; ++i) {
+      xo[i] = descs[i].x_off;
+      mx = std::max(mx, xo[i]);
+      std::copy(b->mem[i]->G0.begin(), b->mem[i]->G0.end(), G0.begin() + (size_t)i * bb);
+      std::copy(b->mem[i]->Gj.begin(), b->mem[i]->Gj.end(), Gj.begin() + (size_t)i * d0.m * bb);
+    }
+    auto up = [&](void** dst, const void* src, size_t bytes) {
+      return cudaMalloc(dst, std::max<size_t>(bytes, 8)) == cudaSuccess &&
+             (bytes == 0 || cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess);
+    };
+    if (!up((void**)&b->dXoffs, xo.data(), n * sizeof(int)) || !up((void**)&b->dG0, G0.data(), G0.size() * sizeof(double)) ||
+        !up((void**)&b->dGj, Gj.data(), (size_t)n * d0.m * bb * sizeof(double)))
+      return bail("upload");
+    BatchLaunch& bl = b->bl;
+    bl.n = n; bl.max_xoff = mx; bl.x_offs = b->dXoffs; bl.G0 = b->dG0; bl.Gj = b->dGj;
+    bl.mem_G0 = (long long)bb; bl.mem_Gj = (long long)d0.m * bb;
+    bl.mem_delta = pb2_dim(h0); bl.mem_jac = pb2_nnz_jac(h0); bl.mem_hess = pb2_nnz_hess(h0);
+    if (h0->alg == PB2_ALG_DMMA) {
+      const size_t ng = h0->plan.gfrag.size(), ne = h0->plan.ell.size(), nn = h0->plan.norms.size();
+      std::vector<double> gf(n * ng), nr(n * nn);
+      std::vector<pb2::EllEntry> el(n * ne);
+      for (int i = 0; i < n; ++i) {
+        std::copy(b->mem[i]->plan.gfrag.begin(), b->mem[i]->plan.gfrag.end(), gf.begin() + i * ng);
+        std::copy(b->mem[i]->plan.norms.begin(), b->mem[i]->plan.norms.end(), nr.begin() + i * nn);
+        std::copy(b->mem[i]->plan.ell.begin(), b->mem[i]->plan.ell.end(), el.begin() + i * ne);
+      }
+      if (!up((void**)&b->dGfrag, gf.data(), gf.size() * sizeof(double)) || !up((void**)&b->dNorms, nr.data(), nr.size() * sizeof(double)) ||
+          !up((void**)&b->dEll, el.data(), el.size() * sizeof(pb2::EllEntry)))
+        return bail("upload");
+      bl.gfrag = b->dGfrag; bl.norms = b->dNorms; bl.ell = b->dEll;
+      bl.mem_gfrag = (long long)ng; bl.mem_norms = (long long)nn; bl.mem_ell = (long long)ne;
+    }
+  }
+  *out = b;
+  return PB2_OK;
+}
+
+int32_t pb2_batch_size(const pb2_batch* b) { return b ? (int32_t)b->mem.size() : -1; }
+int32_t pb2_batch_fused(const pb2_batch* b) { return b ? (b->fused ? 1 : 0) : -1; }
+int64_t pb2_batch_dim(const pb2_batch* b) { return b ? pb2_dim(b->mem[0]) : -1; }
+int64_t pb2_batch_nnz_jac(const pb2_batch* b) { return b ? pb2_nnz_jac(b->mem[0]) : -1; }
+int64_t pb2_batch_nnz_hess(const pb2_batch* b) { return b ? pb2_nnz_hess(b->mem[0]) : -1; }
+int pb2_batch_structure_jac(const pb2_batch* b, int32_t i, int64_t* rows, int64_t* cols) {
+  if (!b || i < 0 || i >= (int)b->mem.size()) return fail(PB2_EINVAL, "pb2_batch_structure_jac: bad member");
+  return pb2_structure_jac(b->mem[i], rows, cols);
+}
+int pb2_batch_structure_hess(const pb2_batch* b, int32_t i, int64_t* rows, int64_t* cols) {
+  if (!b || i < 0 || i >= (int)b->mem.size()) return fail(PB2_EINVAL, "pb2_batch_structure_hess: bad member");
+  return pb2_structure_hess(b->mem[i], rows, cols);
+}
+
+// what == 0: residual + Jacobian (a = delta, c = vals);  1: Hessian (a2 = mu, c = vals)
+static int batch_launch(pb2_batch* b, int what, const double* dZ, double* ddelta, const double* dmu, double* dvals,
+                        cudaStream_t st) {
+  pb2_handle* h0 = b->mem[0];
+  const int n = (int)b->mem.size();
+  if (b->fused) {
+    h0->batch = &b->bl;
+    const int rc = what == 0 ? launch_resjac_core(h0, dZ, ddelta, dvals, st, 0, 0, nullptr, 0, 0) : launch_hess(h0, dZ, dmu, dvals, st);
+    h0->batch = nullptr;
+    return rc;
+  }
+  // members whose kernels cannot share a grid: fork onto the members' own streams, join on `st`
+  const int64_t dim = pb2_dim(h0), nj = pb2_nnz_jac(h0), nh = pb2_nnz_hess(h0);
+  PB2_CUDA(cudaEventRecord(b->fork, st));
+  for (int i = 0; i < n; ++i) {
+    pb2_handle* h = b->mem[i];
+    PB2_CUDA(cudaStreamWaitEvent(h->stream, b->fork, 0));
+    const int rc = what == 0
+        ? launch_resjac(h, dZ, ddelta ? ddelta + (size_t)i * dim : nullptr, dvals ? dvals + (size_t)i * nj : nullptr, h->stream)
+        : launch_hess(h, dZ, dmu + (size_t)i * dim, dvals + (size_t)i * nh, h->stream);
+    if (rc) return rc;
+    PB2_CUDA(cudaEventRecord(b->done[i], h->stream));
+    PB2_CUDA(cudaStreamWaitEvent(st, b->done[i], 0));
+  }
+  return PB2_OK;
+}
+
+int pb2_batch_residual_jacobian_async(pb2_batch* b, const double* dZ, double* ddelta, double* dvals, void* stream) {
+  if (!b || !dZ) return fail(PB2_EINVAL, "pb2_batch_residual_jacobian_async: null argument");
+  DeviceGuard guard(b->mem[0]->d.device);
+  return batch_launch(b, 0, dZ, ddelta, nullptr, dvals, (cudaStream_t)stream);
+}
+
+int pb2_batch_hess_lagrangian_async(pb2_batch* b, const double* dZ, const double* dmu, double* dvals, void* stream) {
+  if (!b || !dZ || !dmu || !dvals) return fail(PB2_EINVAL, "pb2_batch_hess_lagrangian_async: null argument");
+  DeviceGuard guard(b->mem[0]->d.device);
+  return batch_launch(b, 1, dZ, nullptr, dmu, dvals, (cudaStream_t)stream);
+}
+
+static int batch_host(pb2_batch* b, int what, const double* Z, double* delta, const double* mu, double* vals, int space) {
+  pb2_handle* h0 = b->mem[0];
+  DeviceGuard guard(h0->d.device);
+  if (space == PB2_DEVICE) {
+    int rc = batch_launch(b, what, Z, delta, mu, vals, b->stream);
+    if (rc) return rc;
+    PB2_CUDA(cudaStreamSynchronize(b->stream));
+    return PB2_OK;
+  }
+  if (space != PB2_HOST) return fail(PB2_EINVAL, "pb2_batch: bad space");
+  const size_t n = b->mem.size(), nZ = (size_t)h0->d.D * h0->d.K;
+  const size_t nD = n * (size_t)pb2_dim(h0), nJ = n * (size_t)pb2_nnz_jac(h0), nH = n * (size_t)pb2_nnz_hess(h0);
+  int rc;
+  if ((rc = aux_ensure(&b->dZ, nZ))) return rc;
+  PB2_CUDA(cudaMemcpyAsync(b->dZ, Z, nZ * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+  if (what == 0) {
+    if ((delta && (rc = aux_ensure(&b->dDelta, nD))) || (vals && (rc = aux_ensure(&b->dJac, nJ)))) return rc;
+    if ((rc = batch_launch(b, 0, b->dZ, delta ? b->dDelta : nullptr, nullptr, vals ? b->dJac : nullptr, b->stream))) return rc;
+    if (delta) PB2_CUDA(cudaMemcpyAsync(delta, b->dDelta, nD * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    if (vals) PB2_CUDA(cudaMemcpyAsync(vals, b->dJac, nJ * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  } else {
+    if ((rc = aux_ensure(&b->dMu, nD)) || (rc = aux_ensure(&b->dHess, nH))) return rc;
+    PB2_CUDA(cudaMemcpyAsync(b->dMu, mu, nD * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    if ((rc = batch_launch(b, 1, b->dZ, nullptr, b->dMu, b->dHess, b->stream))) return rc;
+    PB2_CUDA(cudaMemcpyAsync(vals, b->dHess, nH * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  }
+  PB2_CUDA(cudaStreamSynchronize(b->stream));
+  return PB2_OK;
+}
+
+int pb2_batch_residual_jacobian(pb2_batch* b, const double* Z, double* delta, double* vals, int space) {
+  if (!b || !Z) return fail(PB2_EINVAL, "pb2_batch_residual_jacobian: null argument");
+  return batch_host(b, 0, Z, delta, nullptr, vals, space);
+}
+
+int pb2_batch_hess_lagrangian(pb2_batch* b, const double* Z, const double* mu, double* vals, int space) {
+  if (!b || !Z || !mu || !vals) return fail(PB2_EINVAL, "pb2_batch_hess_lagrangian: null argument");
+  return batch_host(b, 1, Z, nullptr, mu, vals, space);
+}
+
 // ---- rollout (knot_rollout.cuh) --------------------------------------------------------------------------
 static int launch_rollout(pb2_handle* h, const double* dZ, const double* dx0, double* dstates, double* dout3,
                           cudaStream_t st, int z_stable) {
-  const size_t nJ = (size_t)std::max<int64_t>(pb2_nnz_jac(h), 1);
+  const size_t nJ = (size_t)std::max<int64_t>((int64_t)h->nnz_jac_knot() * h->nk(), 1);
   if (!h->dRoJac) PB2_CUDA(cudaMalloc(&h->dRoJac, nJ * sizeof(double)));
-  // the propagators: one residual + Jacobian launch (Jacobian values only) into the handle's scratch
-  int rc = launch_resjac(h, dZ, nullptr, h->dRoJac, st, 0, 0, nullptr, 0, z_stable);
+  // the propagators: one residual + Jacobian launch (canonical Jacobian values only) into the handle's scratch
+  int rc = launch_resjac_td(h, dZ, nullptr, h->dRoJac, st, 0, 0, nullptr, 0, z_stable);
   if (rc) return rc;
   pb2::RolloutParams q{};
   q.b = h->d.b; q.n_b = h->d.n_b; q.K = h->d.K; q.D = h->d.D; q.x_off = h->d.x_off;
@@ -1165,6 +1461,51 @@ int pb2_host_alloc(void** ptr, int64_t bytes) {
 int pb2_host_free(void* ptr) {
   if (!ptr) return PB2_OK;
   PB2_CUDA(cudaFreeHost(ptr));
+  return PB2_OK;
+}
+
+// ---- gather buffers for a sharded trajectory, set up without any other CUDA binding (one process per GPU) ----
+int pb2_device_alloc(void** ptr, int64_t bytes, int32_t device) {
+  if (!ptr || bytes < 0) return fail(PB2_EINVAL, "pb2_device_alloc: bad argument");
+  DeviceGuard guard(device);
+  PB2_CUDA(cudaMalloc(ptr, (size_t)std::max<int64_t>(bytes, 8)));
+  PB2_CUDA(cudaMemset(*ptr, 0, (size_t)std::max<int64_t>(bytes, 8)));
+  return PB2_OK;
+}
+
+int pb2_device_free(void* ptr) {
+  if (!ptr) return PB2_OK;
+  PB2_CUDA(cudaFree(ptr));
+  return PB2_OK;
+}
+
+int pb2_device_copy(void* dst, const void* src, int64_t bytes) {
+  if (!dst || !src || bytes < 0) return fail(PB2_EINVAL, "pb2_device_copy: bad argument");
+  PB2_CUDA(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDefault));
+  return PB2_OK;
+}
+
+int pb2_ipc_export(const void* dptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == PB2_IPC_HANDLE_BYTES, "handle size");
+  if (!dptr || !handle64) return fail(PB2_EINVAL, "pb2_ipc_export: null argument");
+  cudaIpcMemHandle_t hd;
+  PB2_CUDA(cudaIpcGetMemHandle(&hd, const_cast<void*>(dptr)));
+  std::memcpy(handle64, &hd, sizeof hd);
+  return PB2_OK;
+}
+
+int pb2_ipc_open(const void* handle64, int32_t device, void** dptr) {
+  if (!dptr || !handle64) return fail(PB2_EINVAL, "pb2_ipc_open: null argument");
+  DeviceGuard guard(device);
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle64, sizeof hd);
+  PB2_CUDA(cudaIpcOpenMemHandle(dptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return PB2_OK;
+}
+
+int pb2_ipc_close(void* dptr) {
+  if (!dptr) return PB2_OK;
+  PB2_CUDA(cudaIpcCloseMemHandle(dptr));
   return PB2_OK;
 }
 
@@ -1300,11 +1641,6 @@ int pb2_aux_residual_jacobian_async(pb2_aux* h, const double* dZ, double* ddelta
   return aux_launch(h, dZ, nullptr, ddelta, dvals, nullptr, (cudaStream_t)stream);
 }
 
-static int aux_ensure(double** dev, size_t n) {
-  if (!*dev) PB2_CUDA(cudaMalloc(dev, std::max<size_t>(n, 1) * sizeof(double)));
-  return PB2_OK;
-}
-
 int pb2_aux_residual_jacobian(pb2_aux* h, const double* Z, double* delta, double* vals, int space) {
   if (!h || !Z) return fail(PB2_EINVAL, "pb2_aux_residual_jacobian: null argument");
   DeviceGuard guard_13(h->d.device);
@@ -1363,9 +1699,10 @@ struct pb2_obj {
   pb2::ObjParams p{};
   cudaStream_t stream = nullptr;
   std::vector<void*> owned;            // device allocations behind p
-  double *dZ = nullptr, *dGrad = nullptr, *dJ = nullptr;
+  double *dZ = nullptr, *dGrad = nullptr, *dJ = nullptr, *dHess = nullptr;
   double* hJ = nullptr;                // pinned
   size_t smem = 0;
+  std::vector<int64_t> hrows, hcols;   // Hessian structure (1-based, upper triangle)
 };
 
 extern "C++" {
@@ -1451,6 +1788,52 @@ static int obj_build(pb2_obj* h, const pb2_obj_desc& d) {
   const unsigned int* cp = nullptr;
   if ((rc = obj_upload(h, cz, &cp))) return rc;
   p.counter = const_cast<unsigned int*>(cp);
+  // Hessian structure, in the order knot_objective_hess_kernel writes the values
+  std::vector<int> t_kind(std::max(d.n_terms, 1), 0);
+  for (int t = 0; t < d.n_terms; ++t) {
+    bool dense = false, diag = false;
+    for (int i = t_off[t]; i < t_off[t + 1]; ++i) {
+      dense = dense || a_re[i] != 0.0 || a_im[i] != 0.0;
+      diag = diag || a_sq[i] != 0.0;
+    }
+    t_kind[t] = dense ? 2 : (diag ? 1 : 0);
+  }
+  std::vector<long long> hess_ptr(1, 0);
+  for (int k = 0; k < K; ++k) {
+    const int64_t base = (int64_t)k * d.D + 1;
+    for (auto& it : per_knot[k]) {
+      const int t = it.first, o0 = t_off[t], n = t_off[t + 1] - o0;
+      if (t_kind[t] == 1)
+        for (int i = 0; i < n; ++i) {
+          h->hrows.push_back(base + rows[o0 + i]);
+          h->hcols.push_back(base + rows[o0 + i]);
+        }
+      if (t_kind[t] == 2)
+        for (int j = 0; j < n; ++j)
+          for (int i = 0; i <= j; ++i) {
+            h->hrows.push_back(base + std::min(rows[o0 + i], rows[o0 + j]));
+            h->hcols.push_back(base + std::max(rows[o0 + i], rows[o0 + j]));
+          }
+    }
+    for (int r = 0; r < d.n_regs; ++r) {
+      if (r_w[(size_t)r * K + k] == 0.0) continue;
+      const int o0 = r_off[r], n = r_off[r + 1] - o0;
+      for (int i = 0; i < n; ++i) {
+        h->hrows.push_back(base + r_rows[o0 + i]);
+        h->hcols.push_back(base + r_rows[o0 + i]);
+      }
+      if (r_pow[r]) {
+        for (int i = 0; i < n; ++i) {
+          h->hrows.push_back(base + std::min(r_rows[o0 + i], d.dt_off));
+          h->hcols.push_back(base + std::max(r_rows[o0 + i], d.dt_off));
+        }
+        h->hrows.push_back(base + d.dt_off);
+        h->hcols.push_back(base + d.dt_off);
+      }
+    }
+    hess_ptr.push_back((long long)h->hrows.size());
+  }
+  if ((rc = obj_upload(h, t_kind, &p.t_kind)) || (rc = obj_upload(h, hess_ptr, &p.hess_ptr))) return rc;
   return PB2_OK;
 }
 
@@ -1501,7 +1884,8 @@ int pb2_obj_create(const pb2_obj_desc* desc, pb2_obj** out) {
   int rc = obj_build(h, d);
   if (!rc && h->smem > 200 * 1024) rc = fail(PB2_EINVAL, "pb2_obj_create: knot column too large for shared memory");
   // (function attribute, process-wide: always the device limit -- see pb2_create)
-  if (!rc && raise_dynamic_smem(pb2::knot_objective_kernel) != cudaSuccess)
+  if (!rc && (raise_dynamic_smem(pb2::knot_objective_kernel) != cudaSuccess ||
+              raise_dynamic_smem(pb2::knot_objective_hess_kernel) != cudaSuccess))
     rc = fail(PB2_ECUDA, "pb2_obj_create: cudaFuncSetAttribute failed");
   if (!rc && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
     rc = fail(PB2_ECUDA, "pb2_obj_create: cudaStreamCreate failed");
@@ -1520,7 +1904,7 @@ void pb2_obj_destroy(pb2_obj* h) {
   DeviceGuard guard_d(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (void* q : h->owned) cudaFree(q);
-  for (double* q : {h->dZ, h->dGrad, h->dJ})
+  for (double* q : {h->dZ, h->dGrad, h->dJ, h->dHess})
     if (q) cudaFree(q);
   if (h->hJ) cudaFreeHost(h->hJ);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -1533,6 +1917,50 @@ static int obj_launch(pb2_obj* h, const double* dZ, double* dJ, double* dgrad, c
   p.Z = dZ; p.J = dJ; p.grad = dgrad;
   pb2::knot_objective_kernel<<<h->K, pb2::kObjThreads, h->smem, st>>>(p);
   PB2_CUDA(cudaGetLastError());
+  return PB2_OK;
+}
+
+int64_t pb2_obj_nnz_hess(const pb2_obj* h) { return h ? (int64_t)h->hrows.size() : -1; }
+
+int pb2_obj_structure_hess(const pb2_obj* h, int64_t* rows, int64_t* cols) {
+  if (!h || !rows || !cols) return fail(PB2_EINVAL, "pb2_obj_structure_hess: null argument");
+  std::copy(h->hrows.begin(), h->hrows.end(), rows);
+  std::copy(h->hcols.begin(), h->hcols.end(), cols);
+  return PB2_OK;
+}
+
+static int obj_launch_hess(pb2_obj* h, const double* dZ, double sigma, double* dvals, cudaStream_t st) {
+  if (h->hrows.empty()) return PB2_OK;
+  pb2::ObjParams p = h->p;
+  p.Z = dZ; p.hess = dvals; p.sigma = sigma;
+  pb2::knot_objective_hess_kernel<<<h->K, pb2::kObjThreads, h->smem, st>>>(p);
+  PB2_CUDA(cudaGetLastError());
+  return PB2_OK;
+}
+
+int pb2_obj_hessian_async(pb2_obj* h, const double* dZ, double sigma, double* dvals, void* stream) {
+  if (!h || !dZ || !dvals) return fail(PB2_EINVAL, "pb2_obj_hessian_async: null argument");
+  DeviceGuard guard(h->device);
+  return obj_launch_hess(h, dZ, sigma, dvals, (cudaStream_t)stream);
+}
+
+int pb2_obj_hessian(pb2_obj* h, const double* Z, double sigma, double* vals, int space) {
+  if (!h || !Z || !vals) return fail(PB2_EINVAL, "pb2_obj_hessian: null argument");
+  DeviceGuard guard(h->device);
+  if (space == PB2_DEVICE) {
+    int rc = obj_launch_hess(h, Z, sigma, vals, h->stream);
+    if (rc) return rc;
+    PB2_CUDA(cudaStreamSynchronize(h->stream));
+    return PB2_OK;
+  }
+  if (space != PB2_HOST) return fail(PB2_EINVAL, "pb2_obj_hessian: bad space");
+  const size_t nZ = (size_t)h->D * h->K, nH = h->hrows.size();
+  int rc;
+  if ((rc = aux_ensure(&h->dZ, nZ)) || (rc = aux_ensure(&h->dHess, nH))) return rc;
+  PB2_CUDA(cudaMemcpyAsync(h->dZ, Z, nZ * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if ((rc = obj_launch_hess(h, h->dZ, sigma, h->dHess, h->stream))) return rc;
+  PB2_CUDA(cudaMemcpyAsync(vals, h->dHess, nH * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  PB2_CUDA(cudaStreamSynchronize(h->stream));
   return PB2_OK;
 }
 

@@ -198,7 +198,7 @@ class B200BilinearIntegrator:
 
     def __init__(self, kind, G_drift, G_drives, *, K, D, x_off, dt_off, u_off, x_name="x",
                  u_name="u", device=0, algorithm="auto", knot0=0, global_dim=0, n_states=1,
-                 t_off=None, modulations=None, modulation_derivs=None):
+                 t_off=None, modulations=None, modulation_derivs=None, dense_blocks=False):
         self._lib = capi.load_library()
         G0 = np.asfortranarray(G_drift, dtype=np.float64)
         b = G0.shape[0]
@@ -233,7 +233,8 @@ class B200BilinearIntegrator:
                           self.u_off, self.global_dim, self.knot0, self.device, capi.ALG[algorithm],
                           G0.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                           Gj.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                          self.t_off, 1 if self.time_dependent else 0)
+                          self.t_off, 1 if self.time_dependent else 0, 1 if dense_blocks else 0)
+        self.dense_blocks = bool(dense_blocks)
         h = ctypes.c_void_p()
         capi.check(self._lib.pb2_create(ctypes.byref(d), ctypes.byref(h)))
         self._h = h
@@ -408,6 +409,95 @@ class B200BilinearIntegrator:
         return int(self._lib.pb2_launch_count(self._h))
 
 
+class B200IntegratorBatch:
+    """All integrators of an ensemble (SamplingTrajectory members, or the states of a Multi*Trajectory) in ONE launch.
+
+    The reference attaches one BilinearIntegrator per member and state (integrators.jl:102-117, 134-226); Ipopt's
+    callbacks then walk the vector.  For the small systems those problems use, that is one launch latency per
+    member; here the member is a grid axis.  Outputs are member-major: ``delta[i]``, ``vals[i]`` are what member
+    ``i``'s own integrator would return, bit for bit."""
+
+    def __init__(self, kind, generators, *, K, D, x_offs, dt_off, u_off, device=0, algorithm="auto",
+                 global_dim=0, n_states=1, names=None):
+        self._lib = capi.load_library()
+        n = len(generators)
+        if n < 1 or len(x_offs) != n:
+            raise ValueError("one (G_drift, G_drives) pair and one x_off per member")
+        keep, descs = [], (capi.pb2_desc * n)()
+        dp = ctypes.POINTER(ctypes.c_double)
+        for i, ((G_drift, G_drives), xo) in enumerate(zip(generators, x_offs)):
+            G0 = np.asfortranarray(G_drift, dtype=np.float64)
+            b, m = G0.shape[0], len(G_drives)
+            Gj = (np.concatenate([np.asfortranarray(g, dtype=np.float64).reshape(-1, order="F")
+                                  for g in G_drives]) if m else np.zeros(1))
+            keep += [G0, Gj]
+            n_b = b // 2 if kind == "unitary" else int(n_states)
+            descs[i] = capi.pb2_desc(capi.KIND[kind], b, n_b, m, int(K), int(D), int(xo), int(dt_off), int(u_off),
+                                     int(global_dim), 0, int(device), capi.ALG[algorithm],
+                                     G0.ctypes.data_as(dp), Gj.ctypes.data_as(dp), 0, 0, 0)
+        h = ctypes.c_void_p()
+        capi.check(self._lib.pb2_batch_create(descs, n, ctypes.byref(h)))
+        self._h = h
+        self.n_members = n
+        self.kind, self.K, self.D = kind, int(K), int(D)
+        self.x_offs = [int(x) for x in x_offs]
+        self.names = list(names) if names is not None else [f"x{i}" for i in range(n)]
+        self.dim = int(self._lib.pb2_batch_dim(h))
+        self.nnz_jac = int(self._lib.pb2_batch_nnz_jac(h))
+        self.nnz_hess = int(self._lib.pb2_batch_nnz_hess(h))
+        self.fused = bool(self._lib.pb2_batch_fused(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.pb2_batch_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _structure(self, fn, i, n):
+        rows, cols = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+        ip = ctypes.POINTER(ctypes.c_int64)
+        capi.check(fn(self._h, int(i), rows.ctypes.data_as(ip), cols.ctypes.data_as(ip)))
+        return rows, cols
+
+    def jacobian_structure(self, member):
+        return self._structure(self._lib.pb2_batch_structure_jac, member, self.nnz_jac)
+
+    def hessian_structure(self, member):
+        return self._structure(self._lib.pb2_batch_structure_hess, member, self.nnz_hess)
+
+    def _Z(self, Z):
+        Z = Z.data if isinstance(Z, NamedTrajectory) else Z
+        Z = np.asarray(Z, dtype=np.float64)
+        if Z.size != self.D * self.K:
+            raise ValueError("trajectory size does not match the batch")
+        return np.ascontiguousarray(Z.reshape(-1, order="F") if Z.ndim == 2 else Z)
+
+    def residual_jacobian(self, Z):
+        """-> (delta [n_members, dim], vals [n_members, nnz_jac])"""
+        Z = self._Z(Z)
+        delta = np.empty((self.n_members, self.dim))
+        vals = np.empty((self.n_members, self.nnz_jac))
+        capi.check(self._lib.pb2_batch_residual_jacobian(self._h, _as_ptr(Z), _as_ptr(delta), _as_ptr(vals), capi.PB2_HOST))
+        return delta, vals
+
+    def hessian_values(self, Z, mu):
+        """mu: [n_members, dim] multipliers -> vals [n_members, nnz_hess]"""
+        Z = self._Z(Z)
+        mu = np.ascontiguousarray(mu, dtype=np.float64)
+        if mu.size != self.n_members * self.dim:
+            raise ValueError("one multiplier per constraint row of every member")
+        vals = np.empty((self.n_members, self.nnz_hess))
+        capi.check(self._lib.pb2_batch_hess_lagrangian(self._h, _as_ptr(Z), _as_ptr(mu), _as_ptr(vals), capi.PB2_HOST))
+        return vals
+
+    def residual_jacobian_device(self, dZ, ddelta, dvals, stream=None):
+        capi.check(self._lib.pb2_batch_residual_jacobian_async(self._h, dZ, ddelta, dvals, stream))
+
+    def hessian_device(self, dZ, dmu, dvals, stream=None):
+        capi.check(self._lib.pb2_batch_hess_lagrangian_async(self._h, dZ, dmu, dvals, stream))
+
+
 class B200KnotLinearConstraints:
     """Every ``DerivativeIntegrator(x, xdot, traj)`` of a problem plus the time-consistency constraint and
     ``TimeStepsAllEqualConstraint`` (``timesteps_all_equal=True``, _problem_templates.jl:175-180),
@@ -488,6 +578,21 @@ def BilinearIntegrator(qtraj, traj_or_N, traj=None, **kw):
     the reference rebuilds it from ``qtraj`` and ``N``, here it is passed in."""
     if isinstance(traj_or_N, NamedTrajectory):
         traj = traj_or_N
+    if kw.pop("batched", False):
+        # one launch for every member / state integrator of the problem (member = a grid axis)
+        if not isinstance(qtraj, (MultiKetTrajectory, MultiDensityTrajectory, SamplingTrajectory)) or traj is None:
+            raise TypeError("batched=True needs a multi-state trajectory or an ensemble and its NamedTrajectory")
+        if isinstance(qtraj, SamplingTrajectory):
+            systems = [s_ for s_ in qtraj.systems for _ in range(qtraj.n_substates)]
+        else:
+            systems = [qtraj.system] * len(qtraj.state_names)
+        if any(s_.time_dependent for s_ in systems):
+            raise TypeError("batched=True does not take time-dependent systems")
+        comps = traj.components
+        return B200IntegratorBatch(
+            qtraj.kind, [s_.G_parts() for s_ in systems], K=traj.N, D=traj.dim,
+            x_offs=[comps[n].start for n in qtraj.state_names], dt_off=comps[traj.timestep].start,
+            u_off=comps["u"].start, global_dim=traj.global_dim, names=qtraj.state_names, **kw)
     if kw.pop("fused", False):
         # every state of a MultiKetTrajectory obeys the same generator and the blocks are contiguous in
         # the knot column, so one integrator (one launch) can evaluate them all: rows are knot-major,

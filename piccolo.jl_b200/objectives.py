@@ -127,6 +127,27 @@ class B200Objective:
         capi.check(self._lib.pb2_obj_value_gradient(h, Z.ctypes.data, ctypes.byref(J), g.ctypes.data, capi.PB2_HOST))
         return J.value, g
 
+    def hessian_structure(self):
+        """1-based (rows, cols) of the upper-triangle COO entries ``hessian_values`` fills (duplicates sum)."""
+        h = self._handle()
+        n = int(self._lib.pb2_obj_nnz_hess(h))
+        rows, cols = np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+        ip = ctypes.POINTER(ctypes.c_int64)
+        capi.check(self._lib.pb2_obj_structure_hess(h, rows.ctypes.data_as(ip), cols.ctypes.data_as(ip)))
+        return rows, cols
+
+    def hessian_values(self, Z, sigma=1.0):
+        """Values of sigma * d2J/dz2 (Ipopt's eval_h objective part) in ``hessian_structure`` order."""
+        Z = self._Z(Z)
+        h = self._handle()
+        vals = np.empty(int(self._lib.pb2_obj_nnz_hess(h)))
+        capi.check(self._lib.pb2_obj_hessian(h, Z.ctypes.data, float(sigma), vals.ctypes.data, capi.PB2_HOST))
+        return vals
+
+    def hessian_device(self, dZ, sigma, dvals, stream=None):
+        h = self._handle()
+        capi.check(self._lib.pb2_obj_hessian_async(h, _as_ptr(dZ), float(sigma), _as_ptr(dvals), _as_ptr(stream)))
+
     def value_gradient_device(self, dZ, dJ, dgrad, stream=None):
         """Device pointers / torch CUDA tensors; asynchronous on ``stream``."""
         h = self._handle()

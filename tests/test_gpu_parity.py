@@ -244,6 +244,44 @@ def test_full_size_c5_eight_thousand_knots():
     B.close()
 
 
+def test_c_program_through_the_abi():
+    """tests/c/test_capi.c: a plain C program (no Python, no ctypes) that includes include/piccolo_b200.h, links
+    libpiccolo_b200.so and evaluates BASELINE config C1 through every entry point, against the CPU port."""
+    import os
+    import subprocess
+    cdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c")
+    CP.lib()                                                      # the checker library exists
+    subprocess.check_call(["make", "-C", cdir, "-B", "test_capi"])
+    r = subprocess.run([os.path.join(cdir, "test_capi")], capture_output=True, text=True)
+    assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout + r.stderr
+
+
+def test_dense_blocks_layout():
+    """pb2_desc.dense_blocks: the d/dx_k block as the full n_x x n_x block, zeros included -- the same
+    sparse matrix as the canonical I (x) E layout, entry for entry, for every kind."""
+    for cfg, K in ((3, 40), (2, 12), (6, 9), (4, 11)):
+        p, Z, mu = C.trajectory(cfg, K)
+        Bc, Bd = make(p), make(p, dense_blocks=True)
+        assert Bd.nnz_jac == (p.K - 1) * (p.n_x * p.n_x + (p.m + 2) * p.n_x)
+        Jc, Jd = pb.eval_jacobian(Bc, Z).toarray(), pb.eval_jacobian(Bd, Z).toarray()
+        assert np.array_equal(Jc, Jd)
+        r, c = Bd.jacobian_structure()
+        assert r.size == Bd.nnz_jac and len(set(zip(r.tolist(), c.tolist()))) == r.size      # no duplicates
+        dc, vc = Bc.residual_jacobian(Z)
+        dd, vd = Bd.residual_jacobian(Z)
+        assert np.array_equal(dc, dd)
+        Vd = vd.reshape(p.K - 1, -1)
+        blk = Vd[:, :p.n_x * p.n_x].reshape(-1, p.n_x, p.n_x)      # [knot][col][row]
+        for a in range(p.n_b):
+            for bq in range(p.n_b):
+                sub = blk[:, a * p.b:(a + 1) * p.b, bq * p.b:(bq + 1) * p.b]
+                if a != bq:
+                    assert np.all(sub == 0.0)
+        assert np.array_equal(Vd[:, p.n_x * p.n_x:], vc.reshape(p.K - 1, -1)[:, p.n_b * p.b * p.b:])
+        Bc.close()
+        Bd.close()
+
+
 def test_live_handles_are_independent():
     """Distinct handles are independent (include/piccolo_b200.h): creating a handle for a small problem while a
     handle for a large one is alive must not disturb the large one's launches (the dynamic shared-memory cap is a
@@ -1364,3 +1402,195 @@ def test_reference_sampling_ensemble_test_items():
     Jm = pb.eval_jacobian(B, traj)
     assert Jm.shape == (B.dim, traj.dim * traj.N + traj.global_dim)
     B.close()
+
+
+def _ensemble(cfg, K, n, rng):
+    """n members of config `cfg` with perturbed drifts, their state blocks stacked at the top of the knot column
+    (the layout SamplingTrajectory builds: sampling_problem.jl:389-395), sharing the dt / u rows."""
+    import dataclasses
+    p0, Z0, _ = C.trajectory(cfg, K)
+    n_x, rest = p0.n_x, p0.D - p0.n_x
+    D = n * n_x + rest
+    Z = np.zeros((D, K), order="F")
+    Z[n * n_x:, :] = Z0[n_x:, :]
+    probs = []
+    for i in range(n):
+        Z[i * n_x:(i + 1) * n_x, :] = Z0[:n_x, :] + 1e-3 * rng.standard_normal((n_x, K))
+        probs.append(dataclasses.replace(p0, G0=p0.G0 * (1.0 + 0.03 * i), D=D, x_off=i * n_x,
+                                         dt_off=n * n_x + (p0.dt_off - n_x), u_off=n * n_x + (p0.u_off - n_x)))
+    return probs, Z
+
+
+@pytest.mark.parametrize("cfg,K,n,alg,fused", [(1, 40, 16, "auto", True), (2, 33, 16, "auto", True),
+                                               (4, 25, 5, "auto", True), (6, 30, 7, "auto", True),
+                                               (2, 20, 3, "generic", True), (3, 12, 3, "auto", False)])
+def test_ensemble_batch_one_launch(cfg, K, n, alg, fused):
+    """every member integrator of an ensemble in ONE launch (member = a grid axis).  Each
+    member's rows are checked against the oracle and, bit for bit, against the member's own integrator."""
+    rng = np.random.default_rng(100 + cfg)
+    probs, Z = _ensemble(cfg, K, n, rng)
+    p0 = probs[0]
+    batch = pb.B200IntegratorBatch(p0.kind, [(p.G0, list(p.Gj)) for p in probs], K=K, D=p0.D,
+                                   x_offs=[p.x_off for p in probs], dt_off=p0.dt_off, u_off=p0.u_off, algorithm=alg)
+    assert batch.n_members == n and batch.fused == fused and batch.dim == p0.dim
+    mu = rng.standard_normal((n, p0.dim))
+    d, v = batch.residual_jacobian(Z)
+    h = batch.hessian_values(Z, mu)
+    for i, p in enumerate(probs):
+        assert np.abs(d[i] - KN.residual(p, Z)).max() < RES_TOL
+        assert np.abs(v[i] - KN.jacobian_values(p, Z)).max() < JAC_TOL
+        ho = KN.hessian_values(p, Z, mu[i])
+        assert np.abs(h[i] - ho).max() < HESS_RTOL * max(1.0, np.abs(ho).max())
+        B = make(p, alg)
+        di, vi = B.residual_jacobian(Z)
+        assert np.array_equal(d[i], di) and np.array_equal(v[i], vi)
+        assert np.array_equal(h[i], B.hessian_values(Z, mu[i]))
+        for got, want in ((batch.jacobian_structure(i), B.jacobian_structure()),
+                          (batch.hessian_structure(i), B.hessian_structure())):
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1])
+        B.close()
+    batch.close()
+
+
+def test_ensemble_batch_through_the_plugin_interface():
+    """BilinearIntegrator(SamplingTrajectory, traj, batched=True): the reference's constructor shape
+    (integrators.jl:134-226) returning the one-launch object; members that differ in shape are refused."""
+    X, Y, Zp = np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1.0, -1.0])
+    members = [pb.QuantumSystem(w * Zp, [X, Y], [1.0, 1.0]) for w in (1.0, 1.05, 1.1, 0.9)]
+    st = pb.SamplingTrajectory(pb.KetTrajectory, members)
+    rng = np.random.default_rng(5)
+    K, n_x, m = 21, 4, 2
+    Zs = np.asfortranarray(0.3 * rng.standard_normal((4 * n_x + 2 + 3 * m, K)))
+    Zs[4 * n_x, :] = 0.1 + 0.05 * rng.random(K)
+    traj = pb.NamedTrajectory.multi_state_layout(Zs, st.state_names, n_x, m)
+    batch = pb.BilinearIntegrator(st, traj, batched=True)
+    singles = pb.BilinearIntegrator(st, traj)
+    d, v = batch.residual_jacobian(traj)
+    assert batch.names == st.state_names and batch.fused
+    for i, B in enumerate(singles):
+        di, vi = B.residual_jacobian(traj)
+        assert np.array_equal(d[i], di) and np.array_equal(v[i], vi)
+        B.close()
+    batch.close()
+    with pytest.raises(pb.PB2Error):
+        pb.B200IntegratorBatch("ket", [(np.zeros((4, 4)), []), (np.zeros((6, 6)), [])], K=5, D=20, x_offs=[0, 4],
+                               dt_off=10, u_off=12)
+
+
+def _dense_from_coo(rows, cols, vals, n):
+    import scipy.sparse as sp
+    U = sp.coo_matrix((vals, (rows - 1, cols - 1)), shape=(n, n)).toarray()     # duplicates sum, like Ipopt
+    assert (rows <= cols).all()
+    return U + np.triu(U, 1).T
+
+
+def test_objective_hessian_matches_oracle():
+    """the objective part of eval_h (sigma * d2J) on the device.  Terminal-loss blocks against the
+    oracle's complex-form Hessians, regularizer blocks against its analytic ones; sigma scales everything."""
+    from oracle import objectives as OB
+    rng = np.random.default_rng(77)
+    cplx = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    # the reference's converged unitary solution: infidelity + the regularizers SmoothPulseProblem assembles
+    p, Z = GU.load("trajectories_unitary")
+    names = {"Ũ⃗": range(p.x_off, p.x_off + p.n_x), "Δt": range(p.dt_off, p.dt_off + 1),
+             "u": range(p.u_off, p.u_off + p.m), "du": range(p.u_off + p.m, p.u_off + 2 * p.m)}
+    traj = pb.NamedTrajectory(Z, names)
+    n = p.b // 2
+    Ug = np.linalg.qr(cplx(n, n))[0]
+    J = (pb.UnitaryInfidelityObjective(Ug, "Ũ⃗", traj, Q=100.0) + pb.QuadraticRegularizer("u", traj, 1e-2, dt_power=2)
+         + pb.QuadraticRegularizer("du", traj, [0.5] * p.m, dt_power=1) + pb.QuadraticRegularizer("Δt", traj, 2.0, dt_power=2)
+         + pb.LeakageObjective([1, 3], "Ũ⃗", traj, times=[0, 3, p.K - 1], Qs=[1.0, 2.0, 0.5]))
+    rows, cols = J.hessian_structure()
+    nz = p.K * p.D
+    for sigma in (1.0, 0.37):
+        H = _dense_from_coo(rows, cols, J.hessian_values(Z, sigma), nz)
+        Ho = np.zeros((nz, nz))
+        xs = slice((p.K - 1) * p.D + p.x_off, (p.K - 1) * p.D + p.x_off + p.n_x)
+        Ho[xs, xs] += OB.hessian_from_gradient(lambda y: OB.unitary_infidelity(y, Ug, 100.0)[1], Z[p.x_off:p.x_off + p.n_x, -1])
+        for t, q in zip([0, 3, p.K - 1], [1.0, 2.0, 0.5]):
+            for i in (1, 3):
+                Ho[t * p.D + p.x_off + i, t * p.D + p.x_off + i] += q * 2.0 / 2
+        for name, R, pw in (("u", 1e-2, 2), ("du", 0.5, 1), ("Δt", 2.0, 2)):
+            r = names[name]
+            dvv, dvt, dtt = OB.quadratic_regularizer_hessian(Z[r.start:r.stop], Z[p.dt_off], R, None, pw)
+            for k in range(p.K):
+                for i, row in enumerate(r):
+                    a, b = k * p.D + row, k * p.D + p.dt_off
+                    Ho[a, a] += dvv[i, k]
+                    Ho[a, b] += dvt[i, k]
+                    Ho[b, a] += dvt[i, k]
+                Ho[k * p.D + p.dt_off, k * p.D + p.dt_off] += dtt[k]
+        assert np.abs(H - sigma * Ho).max() < 1e-9 * max(1.0, np.abs(Ho).max())
+    # second difference of the library's own gradient along a random direction (whole-objective consistency)
+    v = rng.standard_normal(nz)
+    v[(p.K - 1) * p.D + p.x_off:(p.K - 1) * p.D + p.x_off + p.n_x] *= 1e-3   # stay on one side of |1 - F|
+    h = 1e-5
+    gp = J.value_gradient((Z.reshape(-1, order="F") + h * v).reshape(Z.shape, order="F"))[1]
+    gm = J.value_gradient((Z.reshape(-1, order="F") - h * v).reshape(Z.shape, order="F"))[1]
+    H1 = _dense_from_coo(rows, cols, J.hessian_values(Z, 1.0), nz)
+    assert np.abs((gp - gm)[:nz] / (2 * h) - H1 @ v).max() < 1e-5 * max(1.0, np.abs(H1 @ v).max())
+    J.close()
+    # a_lin-only objectives have no second derivative; kets give the rank-2 block; device entry point
+    D, K = 8 + 2 + 3, 6
+    Zk = np.asfortranarray(0.4 * rng.standard_normal((D, K)))
+    trk = pb.NamedTrajectory.smooth_pulse_layout(Zk, 8, 1, "ψ̃")
+    psi = cplx(4)
+    psi /= np.linalg.norm(psi)
+    Jk = pb.KetInfidelityObjective(psi, "ψ̃", trk, Q=3.0)
+    Hk = _dense_from_coo(*Jk.hessian_structure(), Jk.hessian_values(Zk), K * D)
+    Hko = OB.hessian_from_gradient(lambda y: OB.ket_infidelity(y, psi, 3.0)[1], Zk[:8, -1])
+    assert np.abs(Hk[(K - 1) * D:(K - 1) * D + 8, (K - 1) * D:(K - 1) * D + 8] - Hko).max() < 1e-10
+    import torch
+    dZ = torch.from_numpy(np.ascontiguousarray(Zk.reshape(-1, order="F"))).cuda()
+    dv = torch.zeros(Jk.hessian_structure()[0].size, dtype=torch.float64, device="cuda")
+    Jk.hessian_device(dZ, 1.0, dv, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(dv.cpu().numpy(), Jk.hessian_values(Zk))
+    Jk.close()
+    rho = np.eye(2) / 2
+    Zd = np.asfortranarray(rng.standard_normal((4 + 2 + 3, 4)))
+    Jd = pb.DensityMatrixInfidelityObjective("ρ⃗̃", rho, pb.NamedTrajectory.smooth_pulse_layout(Zd, 4, 1, "ρ⃗̃"))
+    assert Jd.hessian_structure()[0].size == 0 and Jd.hessian_values(Zd).size == 0
+    Jd.close()
+
+
+def test_two_process_exchange_through_the_c_abi():
+    """peer setup callable from C.  Two processes (both on device 0 here; one per GPU on a
+    multi-GPU box) shard a 3-qubit trajectory using only libpiccolo_b200 for the device side -- pb2_device_alloc,
+    pb2_ipc_export / pb2_ipc_open, pb2_residual_jacobian_exchange_async -- and each ends with every knot's record."""
+    import os
+    import subprocess
+    import sys
+    from tests.ipc_rank import Rank
+    K = 38                                   # 37 knot evaluations: ragged over two ranks
+    env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    child = subprocess.Popen([sys.executable, os.path.join(os.path.dirname(__file__), "ipc_rank.py"), str(K), "0"],
+                             stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, env=env)
+    try:
+        R = Rank(0, K)
+        child.stdin.write(R.export() + "\n")
+        child.stdin.flush()
+        R.open(1, child.stdout.readline().strip())
+        child.stdin.write("go\n")
+        child.stdin.flush()
+        R.run()
+        assert child.stdout.readline().strip() == "done"
+        d, v = R.gathered()
+        p, Z = R.p, R.Z
+        assert np.abs(d - KN.residual(p, Z)).max() < RES_TOL
+        assert np.abs(v - KN.jacobian_values(p, Z)).max() < JAC_TOL
+        B = make(p)
+        d1, v1 = B.residual_jacobian(Z)
+        B.close()
+        assert np.array_equal(d, d1) and np.array_equal(v, v1)      # bitwise what one process computes alone
+        child.stdin.write("check\n")
+        child.stdin.flush()
+        sd, sv = (float(x) for x in child.stdout.readline().split())
+        assert sd == float(np.abs(d).sum()) and sv == float(np.abs(v).sum())
+        child.stdin.write("bye\n")
+        child.stdin.flush()
+        assert child.wait(timeout=60) == 0
+        R.close()
+    finally:
+        if child.poll() is None:
+            child.kill()

@@ -195,3 +195,19 @@ def test_objective_terms_reproduce_the_reference_losses():
     assert len(Jsum.terms) == 3 and len(Jsum.regs) == 1 and Jsum._h is None     # nothing touched the library yet
     with pytest.raises(ValueError):
         J1 + pb.KetInfidelityObjective(g1, "ψ̃1", tk)                           # different trajectory layouts
+
+
+def test_c_program_builds_and_fails_loudly_without_a_gpu():
+    """tests/c/test_capi.c links against libpiccolo_b200.so through the public header alone; on a box without a
+    CUDA device pb2_create refuses (PB2_ENODEVICE) and the program reports it -- there is no CPU path to fall into."""
+    import os
+    import subprocess
+    import torch
+    from oracle import cport as CP
+    cdir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c")
+    CP.lib()
+    subprocess.check_call(["make", "-C", cdir, "-B", "test_capi"], stdout=subprocess.DEVNULL)
+    if torch.cuda.is_available():
+        return                                   # the GPU suite runs the program (tests/test_gpu_parity.py)
+    r = subprocess.run([os.path.join(cdir, "test_capi")], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CUDA device" in r.stdout, r.stdout + r.stderr

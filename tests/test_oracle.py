@@ -344,3 +344,50 @@ def test_objective_gradients_vs_finite_differences():
         f = lambda y: OB.quadratic_regularizer(y[:21].reshape(3, 7), y[21:], [1.0, 2.0, 0.5], dt_power=pw)[0]
         fd = _fd(f, np.concatenate([V.reshape(-1), dt]))
         assert np.abs(np.concatenate([gV.reshape(-1), gdt]) - fd).max() < 1e-6
+
+
+def test_objective_hessians_against_central_differences():
+    """Second derivatives of the objective oracle: hessian_from_gradient is exact for the (piecewise) quadratic
+    losses; here it is checked against an independent second difference of the VALUE, and the regularizer's
+    analytic blocks against differences of its gradient."""
+    from oracle import objectives as OB
+    rng = np.random.default_rng(12)
+    cplx = lambda *s: rng.standard_normal(s) + 1j * rng.standard_normal(s)
+    N = 3
+    Ug = np.linalg.qr(cplx(N, N))[0]
+    x = 0.4 * rng.standard_normal(2 * N * N)
+    for kw in ({}, {"subspace": [0, 2]}):
+        goal = Ug if not kw else np.linalg.qr(cplx(2, 2))[0]
+        f = lambda y: OB.unitary_infidelity(y, goal, 10.0, **kw)
+        H = OB.hessian_from_gradient(lambda y: f(y)[1], x)
+        assert np.abs(H - H.T).max() == 0.0
+        h = 1e-4
+        for (i, j) in ((0, 0), (1, 7), (5, 12), (17, 3)):
+            ei, ej = np.eye(x.size)[i] * h, np.eye(x.size)[j] * h
+            fd = (f(x + ei + ej)[0] - f(x + ei - ej)[0] - f(x - ei + ej)[0] + f(x - ei - ej)[0]) / (4 * h * h)
+            assert abs(fd - H[i, j]) < 1e-5 * max(1.0, abs(H[i, j]))
+    psi = cplx(4)
+    psi /= np.linalg.norm(psi)
+    xk = 0.5 * rng.standard_normal(8)
+    Hk = OB.hessian_from_gradient(lambda y: OB.ket_infidelity(y, psi, 3.0)[1], xk)
+    c = -3.0 * (1.0 if 1 - abs(np.vdot(psi, xk[:4] + 1j * xk[4:])) ** 2 >= 0 else -1.0)
+    a_re, a_im = np.concatenate([psi.real, psi.imag]), np.concatenate([-psi.imag, psi.real])
+    assert np.abs(Hk - 2 * c * (np.outer(a_re, a_re) + np.outer(a_im, a_im))).max() < 1e-9
+    # regularizer: analytic blocks vs differences of its gradient
+    V, dt, R, base = rng.standard_normal((2, 5)), 0.1 + rng.random(5), np.array([0.3, 0.7]), rng.standard_normal((2, 5))
+    for pw in (0, 1, 2):
+        dvv, dvt, dtt = OB.quadratic_regularizer_hessian(V, dt, R, base, pw)
+        h = 1e-6
+        for t in range(5):
+            for i in range(2):
+                Vp, Vm = V.copy(), V.copy()
+                Vp[i, t] += h
+                Vm[i, t] -= h
+                gp, gm = OB.quadratic_regularizer(Vp, dt, R, base, pw), OB.quadratic_regularizer(Vm, dt, R, base, pw)
+                assert abs((gp[1][i, t] - gm[1][i, t]) / (2 * h) - dvv[i, t]) < 1e-7
+                assert abs((gp[2][t] - gm[2][t]) / (2 * h) - dvt[i, t]) < 1e-7
+            dp, dm = dt.copy(), dt.copy()
+            dp[t] += h
+            dm[t] -= h
+            gp, gm = OB.quadratic_regularizer(V, dp, R, base, pw), OB.quadratic_regularizer(V, dm, R, base, pw)
+            assert abs((gp[2][t] - gm[2][t]) / (2 * h) - dtt[t]) < 1e-7
