@@ -460,8 +460,10 @@ def run_ours(args):
         torch.cuda.synchronize()
         h_ms = ev[0].elapsed_time(ev[1]) / hsteps
         hess = {"ms_per_callback": h_ms, "evals_per_sec": n_eval / (h_ms * 1e-3), "nnz_per_knot": B.nnz_hess // max(1, n_eval),
-                "kernel": "knot_u8h_kernel (DMMA forward + adjoint jets)" if (p.b == 16 and p.n_b == 8 and p.m <= 4)
-                else "knot_generic_kernel<2> (second-order Taylor jets in shared memory)"}
+                "kernel": {"u8h": "knot_u8h_kernel (DMMA forward + adjoint jets, 3-qubit shape)",
+                           "dmmah": "knot_dmmah_kernel (DMMA forward tiles: state, first- and second-order jets; adjoint "
+                                    "tiles with the transposed generator)",
+                           "generic": "knot_generic_kernel<2> (second-order Taylor jets in shared memory)"}[B.hessian_algorithm]}
         del gh
 
     # ---- objective value + gradient, device-resident, same graph scheme ----

@@ -107,6 +107,9 @@ int64_t pb2_dim(const pb2_handle* h);
 int64_t pb2_nnz_jac(const pb2_handle* h);
 int64_t pb2_nnz_hess(const pb2_handle* h);
 int32_t pb2_algorithm(const pb2_handle* h); /* the path actually selected */
+/* kernel behind pb2_hess_lagrangian: 0 none (time-dependent handle), 1 shared-memory jet kernel, 2 general tensor-core
+ * kernel (b <= 16, <= 12 column tiles), 3 the 3-qubit tensor-core kernel (16-byte aligned device pointers) */
+int32_t pb2_hessian_algorithm(const pb2_handle* h);
 
 /* COO structure, 1-based, deterministic, computed on the host (no device work).
  * Order documented in DESIGN.md ("canonical COO order"); rows of the Jacobian are

@@ -16,7 +16,7 @@ OPT = {"early_z": 1, "pipelined": 2}
 # every symbol include/piccolo_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "pb2_version", "pb2_last_error", "pb2_device_count", "pb2_create", "pb2_destroy",
-    "pb2_dim", "pb2_nnz_jac", "pb2_nnz_hess", "pb2_algorithm", "pb2_structure_jac",
+    "pb2_dim", "pb2_nnz_jac", "pb2_nnz_hess", "pb2_algorithm", "pb2_hessian_algorithm", "pb2_structure_jac",
     "pb2_structure_hess", "pb2_residual", "pb2_jacobian", "pb2_residual_jacobian",
     "pb2_hess_lagrangian", "pb2_residual_jacobian_async", "pb2_hess_lagrangian_async",
     "pb2_compact_stride", "pb2_residual_jacobian_compact_async", "pb2_expand_compact_async",
@@ -122,6 +122,8 @@ def load_library():
         getattr(L, f).restype = ctypes.c_int64
     L.pb2_algorithm.argtypes = [H]
     L.pb2_algorithm.restype = ctypes.c_int32
+    L.pb2_hessian_algorithm.argtypes = [H]
+    L.pb2_hessian_algorithm.restype = ctypes.c_int32
     L.pb2_structure_jac.argtypes = [H, ip, ip]
     L.pb2_structure_hess.argtypes = [H, ip, ip]
     L.pb2_residual.argtypes = [H, vp, vp, ctypes.c_int]

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +25,7 @@
 #include "knot_dmma.cuh"
 #include "knot_u8.cuh"
 #include "knot_u8h.cuh"
+#include "knot_dmmah.cuh"
 #include "knot_aux.cuh"
 #include "knot_objective.cuh"
 #include "knot_rollout.cuh"
@@ -140,6 +142,10 @@ struct BatchLaunch {
   const double *G0 = nullptr, *Gj = nullptr, *gfrag = nullptr, *norms = nullptr;
   const pb2::EllEntry* ell = nullptr;
   long long mem_G0 = 0, mem_Gj = 0, mem_gfrag = 0, mem_ell = 0, mem_norms = 0, mem_delta = 0, mem_jac = 0, mem_hess = 0;
+  // tensor-core Hessian tables (knot_dmmah.cuh); null: the members run the jet kernel
+  const double *hgfrag = nullptr, *hgfragT = nullptr, *hnorms = nullptr;
+  const pb2::EllEntry *hell = nullptr, *hellT = nullptr;
+  long long mem_hgfrag = 0, mem_hell = 0, mem_hnorms = 0;
 };
 
 struct pb2_handle {
@@ -151,6 +157,10 @@ struct pb2_handle {
   double *dG0 = nullptr, *dGj = nullptr;
   pb2::DmmaPlan plan;          // tensor-core path tables (host copy) and their device mirrors
   double* dGfrag = nullptr;
+  pb2::DmmahPlan hplan;        // tensor-core Hessian (general b <= 16): tables and their device mirrors
+  double *dHGfrag = nullptr, *dHGfragT = nullptr, *dHNorms = nullptr;
+  pb2::EllEntry *dHEll = nullptr, *dHEllT = nullptr;
+  int dmmah = 1;               // PB2_NO_DMMAH=1: Hessian through the jet kernel
   double* dNorms = nullptr;
   double* dTab = nullptr;
   double *dComp = nullptr, *hComp = nullptr;   // compact records: device buffer and pinned landing zone
@@ -158,6 +168,10 @@ struct pb2_handle {
   bool coef_set = false;
   double *dRoJac = nullptr, *dRoStates = nullptr, *dRoX0 = nullptr, *dRoOut = nullptr;   // rollout scratch (lazy)
   cudaEvent_t chunk_ev[16] = {};
+  // host-pointer pipeline: upload, kernel and download of a callback run chunk by chunk on three streams
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t in_ev[16] = {}, k_ev[16] = {};
+  int64_t nk_sub = -1;         // >= 0: this launch evaluates a sub-range of the knots (pointers already offset)
   double* dTables = nullptr;   // [gfrag | norms (even) | theta | 1/k!] contiguous, the u8 kernels' smem order
   long long* dTrace = nullptr;
   long long* dTrace2 = nullptr;
@@ -192,7 +206,7 @@ struct pb2_handle {
   int64_t launches = 0;
 
   int n_x() const { return d.b * d.n_b; }
-  int64_t nk() const { return (int64_t)d.K - 1; }
+  int64_t nk() const { return nk_sub >= 0 ? nk_sub : (int64_t)d.K - 1; }
   // canonical values per knot (what the kernels write) and what the caller sees (dense_blocks: full n_x x n_x block)
   int nnz_jac_knot() const { return d.n_b * d.b * d.b + n_x() * d.m + 2 * n_x() + (d.time_dependent ? n_x() : 0); }
   int nnz_jac_user_knot() const { return d.dense_blocks ? nnz_jac_knot() - d.n_b * d.b * d.b + n_x() * n_x() : nnz_jac_knot(); }
@@ -515,8 +529,35 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
     h->launches++;
     return PB2_OK;
   }
-  {
-    // the Lagrangian Hessian always runs the jet kernel (second-order jets)
+  if (h->hplan.ok && (!bl || bl->hgfrag)) {
+    // general tensor-core Hessian: one CTA per knot, forward + adjoint tiles (knot_dmmah.cuh)
+    const pb2::DmmahPlan& hp = h->hplan;
+    pb2::DmmahParams q{};
+    q.b = p.b; q.n_b = p.n_b; q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
+    q.nnz_hess = p.nnz_hess; q.max_sub = 4096; q.nk = (int)h->nk();
+    q.tiles_f = hp.tiles_f; q.tiles_a = hp.tiles_a;
+    q.Gfrag = h->dHGfrag; q.GfragT = h->dHGfragT; q.ell = h->dHEll; q.ellT = h->dHEllT; q.norms = h->dHNorms;
+    q.Z = dZ; q.mu = dmu; q.hess = dhess;
+    if (bl) {
+      q.mem_n = bl->n; q.x_offs = bl->x_offs;
+      q.Gfrag = bl->hgfrag; q.GfragT = bl->hgfragT; q.ell = bl->hell; q.ellT = bl->hellT; q.norms = bl->hnorms;
+      q.mem_gfrag = bl->mem_hgfrag; q.mem_ell = bl->mem_hell; q.mem_norms = bl->mem_hnorms;
+      q.mem_mu = bl->mem_delta; q.mem_hess = bl->mem_hess;
+    }
+    const size_t smem = pb2::dmmah_layout(q, hp.NT);
+    const int threads = 32 * (hp.tiles_f + hp.tiles_a);
+    pb2::DmmahKernel kern = pb2::dmmah_kernel(hp.NT, hp.W);
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
+      cudaGetLastError();
+      occ = 1;
+    }
+    const int n_mem = bl ? bl->n : 1;
+    const int blocks = (int)std::min<int64_t>(q.nk, std::max(1, h->n_sm * occ / n_mem));
+    kern<<<dim3(blocks, n_mem), threads, smem, st>>>(q);
+    PB2_CUDA(cudaGetLastError());
+  } else {
+    // every other shape: the jet kernel (second-order jets in shared memory)
     const LaunchCfg& c = h->cfg2;
     const int blocks = (int)((h->nk() + c.KPC - 1) / c.KPC);
     pb2::knot_generic_kernel<2, kNT><<<dim3(blocks, bl ? bl->n : 1), kNT, c.smem, st>>>(p, c.GS, c.KPC, c.gj_in_smem);
@@ -701,6 +742,25 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     PB2_CUDA_H(cudaMemcpy(h->dGfrag, h->plan.gfrag.data(), ng, cudaMemcpyHostToDevice));
     PB2_CUDA_H(cudaMemcpy(h->dEll, h->plan.ell.data(), ne, cudaMemcpyHostToDevice));
     PB2_CUDA_H(cudaMemcpy(h->dNorms, h->plan.norms.data(), nn, cudaMemcpyHostToDevice));
+    // the Lagrangian Hessian on the tensor cores too (the 3-qubit shape has its own kernel; time-dependent handles
+    // have no Hessian)
+    h->dmmah = std::getenv("PB2_NO_DMMAH") ? 0 : 1;
+    if (h->dmmah && !d.time_dependent) h->hplan = pb2::dmmah_plan(d.b, d.n_b, d.m, h->G0.data(), h->Gj.data());
+    if (h->hplan.ok) {
+      const pb2::DmmahPlan& hp = h->hplan;
+      const size_t hg = hp.gfrag.size() * sizeof(double), he = hp.ell.size() * sizeof(pb2::EllEntry);
+      PB2_CUDA_H(cudaMalloc(&h->dHGfrag, hg));
+      PB2_CUDA_H(cudaMalloc(&h->dHGfragT, hg));
+      PB2_CUDA_H(cudaMalloc(&h->dHEll, he));
+      PB2_CUDA_H(cudaMalloc(&h->dHEllT, he));
+      PB2_CUDA_H(cudaMalloc(&h->dHNorms, hp.norms.size() * sizeof(double)));
+      PB2_CUDA_H(cudaMemcpy(h->dHGfrag, hp.gfrag.data(), hg, cudaMemcpyHostToDevice));
+      PB2_CUDA_H(cudaMemcpy(h->dHGfragT, hp.gfragT.data(), hg, cudaMemcpyHostToDevice));
+      PB2_CUDA_H(cudaMemcpy(h->dHEll, hp.ell.data(), he, cudaMemcpyHostToDevice));
+      PB2_CUDA_H(cudaMemcpy(h->dHEllT, hp.ellT.data(), he, cudaMemcpyHostToDevice));
+      PB2_CUDA_H(cudaMemcpy(h->dHNorms, hp.norms.data(), hp.norms.size() * sizeof(double), cudaMemcpyHostToDevice));
+      PB2_CUDA_H(raise_dynamic_smem(pb2::dmmah_kernel(hp.NT, hp.W)));
+    }
     double invfact[pb2::kMaxDeg + 1];
     invfact[0] = 1.0;
     for (int q = 1; q <= pb2::kMaxDeg; ++q) invfact[q] = invfact[q - 1] / (double)q;
@@ -804,6 +864,8 @@ void pb2_destroy(pb2_handle* h) {
   for (double* p : {h->dG0, h->dGj, h->dZ, h->dDelta, h->dJac, h->dMu, h->dHess})
     if (p) cudaFree(p);
   if (h->dGfrag) cudaFree(h->dGfrag);
+  for (void* q : {(void*)h->dHGfrag, (void*)h->dHGfragT, (void*)h->dHNorms, (void*)h->dHEll, (void*)h->dHEllT})
+    if (q) cudaFree(q);
   if (h->dEll) cudaFree(h->dEll);
   if (h->dNorms) cudaFree(h->dNorms);
   if (h->dTab) cudaFree(h->dTab);
@@ -821,6 +883,12 @@ void pb2_destroy(pb2_handle* h) {
   if (h->hComp) cudaFreeHost(h->hComp);
   for (cudaEvent_t e : h->chunk_ev)
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->in_ev)
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->k_ev)
+    if (e) cudaEventDestroy(e);
+  if (h->s_in) cudaStreamDestroy(h->s_in);
+  if (h->s_out) cudaStreamDestroy(h->s_out);
   if (h->dTrace) cudaFree(h->dTrace);
   if (h->dTrace2) cudaFree(h->dTrace2);
   if (h->dTrace3) cudaFree(h->dTrace3);
@@ -834,6 +902,14 @@ void pb2_destroy(pb2_handle* h) {
 int64_t pb2_dim(const pb2_handle* h) { return h ? (int64_t)h->n_x() * h->nk() : -1; }
 int64_t pb2_nnz_jac(const pb2_handle* h) { return h ? (int64_t)h->nnz_jac_user_knot() * h->nk() : -1; }
 int64_t pb2_nnz_hess(const pb2_handle* h) { return h ? (int64_t)h->nnz_hess_knot() * h->nk() : -1; }
+// which kernel evaluates the Lagrangian Hessian: 1 = jet kernel, 2 = general tensor-core kernel, 3 = 3-qubit kernel
+int32_t pb2_hessian_algorithm(const pb2_handle* h) {
+  if (!h) return -1;
+  if (h->d.time_dependent) return 0;
+  if (h->u8h_ok && (h->d.D % 2 == 0) && (h->d.x_off % 2 == 0)) return 3;
+  return h->hplan.ok ? 2 : 1;
+}
+
 int32_t pb2_algorithm(const pb2_handle* h) { return h ? h->alg : -1; }
 int64_t pb2_launch_count(const pb2_handle* h) { return h ? h->launches : -1; }
 #ifdef PB2_TRACE
@@ -1058,30 +1134,97 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
     const int n_x = h->n_x(), bb = h->d.b * h->d.b, n_b = h->d.n_b, nJd = (h->d.m + 1) * n_x, nnz = h->nnz_jac_knot();
     if ((rc = ensure(&h->dZ, &h->hZ, nZ))) return rc;
     if ((rc = ensure(&h->dComp, &h->hComp, (size_t)(nk * cs)))) return rc;
-    if ((rc = stage_in(h, Z, h->hZ, h->dZ, nZ))) return rc;
-    if ((rc = launch_resjac(h, h->dZ, nullptr, h->dComp, h->stream, 1, 0, nullptr, 0, 1))) return rc;
+    // Chunk boundaries kb[0..nch]: equal chunks, 8 by default (PB2_D2H_CHUNKS=n overrides).  Measured on C3
+    // (tools/e2e_timeline.py, profiles/r02_e2e_timeline.txt): the records cross PCIe back to back at 45-51 GB/s
+    // (158 us for 7.2 MB) from ~26 us after the call; the host-side replication into the caller's 23.5 MB of COO
+    // values runs at 130-170 GB/s on 16 threads and finishes ~28 us after the last chunk lands.  A small first chunk,
+    // small last chunks, 6, 12 or 16 chunks were all measured and are no better (per-copy overhead, replication lag).
     const int nch_env = std::getenv("PB2_D2H_CHUNKS") ? std::atoi(std::getenv("PB2_D2H_CHUNKS")) : 8;
     const int nch = (int)std::min<int64_t>(std::min(16, std::max(1, nch_env)), std::max<int64_t>(1, nk / 32));
-    const int64_t per = (nk + nch - 1) / nch;
-    for (int c = 0; c < nch; ++c) {
-      const int64_t k0 = c * per, k1 = std::min(nk, k0 + per);
-      if (!h->chunk_ev[c]) PB2_CUDA(cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
-      if (k1 > k0)
-        PB2_CUDA(cudaMemcpyAsync(h->hComp + k0 * cs, h->dComp + k0 * cs, (size_t)(k1 - k0) * cs * sizeof(double),
-                                 cudaMemcpyDeviceToHost, h->stream));
-      PB2_CUDA(cudaEventRecord(h->chunk_ev[c], h->stream));
+    int64_t kb[17];
+    {
+      const int64_t per = (nk + nch - 1) / nch;
+      for (int c = 0; c <= nch; ++c) kb[c] = std::min(nk, c * per);
     }
+    static const bool piped = !(std::getenv("PB2_E2E_PIPE") && std::atoi(std::getenv("PB2_E2E_PIPE")) == 0);
+    const bool tl = std::getenv("PB2_E2E_TIMELINE") != nullptr;     // host-clock stamps on stderr (measurement aid)
+    const auto t0 = std::chrono::steady_clock::now();
+    auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
+    double t_enq = 0.0, t_chunk[16] = {}, t_pool = 0.0;
+    if (piped && nch > 1) {
+      // chunk c: upload its knot columns (s_in) -> evaluate its knots (h->stream) -> download its records (s_out).
+      // The download of the records is the long pole (PCIe, 7 KB per knot); everything else hides under it, and
+      // the first records leave ~one chunk's upload + kernel after the call instead of after the whole kernel.
+      if (!h->s_in) PB2_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+      if (!h->s_out) PB2_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+      const bool direct_in = is_pinned_or_device(Z);
+      const int D = h->d.D;
+      static const int h2d_mode = std::getenv("PB2_E2E_H2D") ? std::atoi(std::getenv("PB2_E2E_H2D")) : 0;
+      for (int c = 0; c < nch; ++c) {
+        const int64_t k0 = kb[c], k1 = kb[c + 1];
+        for (cudaEvent_t* e : {&h->chunk_ev[c], &h->in_ev[c], &h->k_ev[c]})
+          if (!*e) PB2_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        if (k1 > k0) {
+          // knots k0 .. k1-1 read columns k0 .. k1; column k0 came with the previous chunk.
+          // h2d_mode 0: every chunk's columns on s_in;  1: on the compute stream (no events);  2: chunk 0 alone,
+          // then all the rest in one copy (two uploads per call whatever the number of chunks)
+          int64_t c0 = c == 0 ? 0 : k0 + 1, c1 = k1 + 1;
+          if (h2d_mode == 2) {
+            if (c == 1) c1 = nk + 1;
+            if (c >= 2) c1 = c0;
+          }
+          if (c1 > c0) {
+            const double* from = Z + c0 * D;
+            if (!direct_in) {
+              std::memcpy(h->hZ + c0 * D, from, (size_t)(c1 - c0) * D * sizeof(double));
+              from = h->hZ + c0 * D;
+            }
+            cudaStream_t sh = h2d_mode == 1 ? h->stream : h->s_in;
+            PB2_CUDA(cudaMemcpyAsync(h->dZ + c0 * D, from, (size_t)(c1 - c0) * D * sizeof(double), cudaMemcpyHostToDevice, sh));
+            if (h2d_mode != 1) {
+              PB2_CUDA(cudaEventRecord(h->in_ev[c], h->s_in));
+              PB2_CUDA(cudaStreamWaitEvent(h->stream, h->in_ev[c], 0));
+            }
+          }
+          h->nk_sub = k1 - k0;
+          rc = launch_resjac(h, h->dZ + k0 * D, nullptr, h->dComp + k0 * cs, h->stream, 1, 0, nullptr, 0, 1);
+          h->nk_sub = -1;
+          if (rc) return rc;
+          PB2_CUDA(cudaEventRecord(h->k_ev[c], h->stream));
+          PB2_CUDA(cudaStreamWaitEvent(h->s_out, h->k_ev[c], 0));
+          PB2_CUDA(cudaMemcpyAsync(h->hComp + k0 * cs, h->dComp + k0 * cs, (size_t)(k1 - k0) * cs * sizeof(double),
+                                   cudaMemcpyDeviceToHost, h->s_out));
+        }
+        PB2_CUDA(cudaEventRecord(h->chunk_ev[c], h->s_out));
+      }
+    } else {
+      if ((rc = stage_in(h, Z, h->hZ, h->dZ, nZ))) return rc;
+      if ((rc = launch_resjac(h, h->dZ, nullptr, h->dComp, h->stream, 1, 0, nullptr, 0, 1))) return rc;
+      for (int c = 0; c < nch; ++c) {
+        const int64_t k0 = kb[c], k1 = kb[c + 1];
+        if (!h->chunk_ev[c]) PB2_CUDA(cudaEventCreateWithFlags(&h->chunk_ev[c], cudaEventDisableTiming));
+        if (k1 > k0)
+          PB2_CUDA(cudaMemcpyAsync(h->hComp + k0 * cs, h->dComp + k0 * cs, (size_t)(k1 - k0) * cs * sizeof(double),
+                                   cudaMemcpyDeviceToHost, h->stream));
+        PB2_CUDA(cudaEventRecord(h->chunk_ev[c], h->stream));
+      }
+    }
+    if (tl) t_enq = us();
     std::atomic<int> ready[16];
     for (auto& r : ready) r.store(0, std::memory_order_relaxed);
     std::atomic<int> failed{0};
     const double* comp = h->hComp;
-    static const bool nt = std::getenv("PB2_HOST_NT") && std::atoi(std::getenv("PB2_HOST_NT")) != 0;
+    // non-temporal stores pay once the caller's arrays no longer fit the host's caches (C5: 188 MB): no read-for-
+    // ownership traffic; below that they only compete with the DMA writes (C3: slower).  PB2_HOST_NT=0/1 overrides.
+    const bool nt = std::getenv("PB2_HOST_NT") ? std::atoi(std::getenv("PB2_HOST_NT")) != 0
+                                               : (size_t)nk * (size_t)nnz * sizeof(double) > ((size_t)96 << 20);
     auto expand = [&](int64_t a, int64_t b) {
       alignas(16) double E[256];
       alignas(16) double ones[128];
       for (double& o : ones) o = 1.0;
       for (int64_t k = a; k < b; ++k) {
-        const int c = (int)(k / per);
+        int c = 0;
+        while (k >= kb[c + 1]) ++c;
         while (!ready[c].load(std::memory_order_acquire))
           if (failed.load(std::memory_order_relaxed)) return;
         const double* src = comp + k * cs;
@@ -1108,10 +1251,21 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
     for (int c = 0; c < nch; ++c) {
       if (cudaEventSynchronize(h->chunk_ev[c]) != cudaSuccess) { failed.store(1); break; }
       ready[c].store(1, std::memory_order_release);
+      if (tl) t_chunk[c] = us();
     }
     pool.finish();
-    if (failed.load()) return fail(PB2_ECUDA, "pb2_residual_jacobian: device-to-host copy failed");
-    PB2_CUDA(cudaStreamSynchronize(h->stream));
+    if (tl) {
+      t_pool = us();
+      std::fprintf(stderr, "pb2 e2e timeline [us]: enqueued %.1f | chunks landed", t_enq);
+      for (int c = 0; c < nch; ++c) std::fprintf(stderr, " %.1f", t_chunk[c]);
+      std::fprintf(stderr, " | replicated %.1f\n", t_pool);
+    }
+    if (failed.load()) {
+      cudaStreamSynchronize(h->stream);
+      if (h->s_out) cudaStreamSynchronize(h->s_out);
+      return fail(PB2_ECUDA, "pb2_residual_jacobian: device-to-host copy failed");
+    }
+    // (the last chunk's event completed: every upload, kernel and download of this call has)
     return PB2_OK;
   }
   if ((rc = ensure(&h->dZ, &h->hZ, nZ))) return rc;
@@ -1194,6 +1348,8 @@ struct pb2_batch {
   int* dXoffs = nullptr;
   double *dG0 = nullptr, *dGj = nullptr, *dGfrag = nullptr, *dNorms = nullptr;
   pb2::EllEntry* dEll = nullptr;
+  double *dHGfrag = nullptr, *dHGfragT = nullptr, *dHNorms = nullptr;   // tensor-core Hessian tables, member-major
+  pb2::EllEntry *dHEll = nullptr, *dHEllT = nullptr;
   cudaStream_t stream = nullptr;
   std::vector<cudaEvent_t> done;
   cudaEvent_t fork = nullptr;
@@ -1205,6 +1361,8 @@ void pb2_batch_destroy(pb2_batch* b) {
   if (!b->mem.empty()) {
     DeviceGuard guard(b->mem[0]->d.device);
     if (b->stream) cudaStreamSynchronize(b->stream);
+    for (void* q : {(void*)b->dHGfrag, (void*)b->dHGfragT, (void*)b->dHNorms, (void*)b->dHEll, (void*)b->dHEllT})
+      if (q) cudaFree(q);
     for (void* q : {(void*)b->dXoffs, (void*)b->dG0, (void*)b->dGj, (void*)b->dGfrag, (void*)b->dNorms, (void*)b->dEll,
                     (void*)b->dZ, (void*)b->dDelta, (void*)b->dJac, (void*)b->dMu, (void*)b->dHess})
       if (q) cudaFree(q);
@@ -1300,6 +1458,30 @@ int pb2_batch_create(const pb2_desc* descs, int32_t n, pb2_batch** out) {
         return bail("upload");
       bl.gfrag = b->dGfrag; bl.norms = b->dNorms; bl.ell = b->dEll;
       bl.mem_gfrag = (long long)ng; bl.mem_norms = (long long)nn; bl.mem_ell = (long long)ne;
+    }
+    // the Hessian shares a launch on the tensor cores when every member has the same tile plan
+    bool hsame = h0->hplan.ok;
+    for (const pb2_handle* h : b->mem)
+      hsame = hsame && h->hplan.ok && h->hplan.NT == h0->hplan.NT && h->hplan.W == h0->hplan.W &&
+              h->hplan.tiles_f == h0->hplan.tiles_f && h->hplan.tiles_a == h0->hplan.tiles_a;
+    if (hsame) {
+      const size_t ng = h0->hplan.gfrag.size(), ne = h0->hplan.ell.size(), nn = h0->hplan.norms.size();
+      std::vector<double> gf(n * ng), gt(n * ng), nr(n * nn);
+      std::vector<pb2::EllEntry> el(n * ne), et(n * ne);
+      for (int i = 0; i < n; ++i) {
+        const pb2::DmmahPlan& hp = b->mem[i]->hplan;
+        std::copy(hp.gfrag.begin(), hp.gfrag.end(), gf.begin() + i * ng);
+        std::copy(hp.gfragT.begin(), hp.gfragT.end(), gt.begin() + i * ng);
+        std::copy(hp.norms.begin(), hp.norms.end(), nr.begin() + i * nn);
+        std::copy(hp.ell.begin(), hp.ell.end(), el.begin() + i * ne);
+        std::copy(hp.ellT.begin(), hp.ellT.end(), et.begin() + i * ne);
+      }
+      if (!up((void**)&b->dHGfrag, gf.data(), gf.size() * sizeof(double)) || !up((void**)&b->dHGfragT, gt.data(), gt.size() * sizeof(double)) ||
+          !up((void**)&b->dHNorms, nr.data(), nr.size() * sizeof(double)) || !up((void**)&b->dHEll, el.data(), el.size() * sizeof(pb2::EllEntry)) ||
+          !up((void**)&b->dHEllT, et.data(), et.size() * sizeof(pb2::EllEntry)))
+        return bail("upload");
+      bl.hgfrag = b->dHGfrag; bl.hgfragT = b->dHGfragT; bl.hnorms = b->dHNorms; bl.hell = b->dHEll; bl.hellT = b->dHEllT;
+      bl.mem_hgfrag = (long long)ng; bl.mem_hell = (long long)ne; bl.mem_hnorms = (long long)nn;
     }
   }
   *out = b;

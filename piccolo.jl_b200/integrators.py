@@ -242,6 +242,7 @@ class B200BilinearIntegrator:
         self.nnz_jac = int(self._lib.pb2_nnz_jac(h))
         self.nnz_hess = int(self._lib.pb2_nnz_hess(h))
         self.algorithm = {1: "generic", 2: "dmma"}[self._lib.pb2_algorithm(h)]
+        self.hessian_algorithm = {0: None, 1: "generic", 2: "dmmah", 3: "u8h"}[self._lib.pb2_hessian_algorithm(h)]
 
     def close(self):
         if getattr(self, "_h", None):

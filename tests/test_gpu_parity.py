@@ -68,6 +68,9 @@ def test_synthetic_configs_vs_oracle(cfg, K):
             assert B.algorithm == expected_auto(p)
             if cfg in (1, 2, 3, 4):
                 assert B.algorithm == "dmma"          # every BASELINE config ships on the tensor-core path
+                assert B.hessian_algorithm == ("u8h" if cfg == 3 else "dmmah")     # ... the Hessian too
+        else:
+            assert B.hessian_algorithm == "generic"
         check_all(p, Z, mu, B)
         B.close()
 
@@ -1594,3 +1597,96 @@ def test_two_process_exchange_through_the_c_abi():
     finally:
         if child.poll() is None:
             child.kill()
+
+
+def test_host_pointer_pipeline_pinned_and_pageable(monkeypatch):
+    """The host-pointer call of the 3-qubit shape uploads, evaluates and downloads chunk by chunk on three streams
+    (pb2_api.cu): pinned caller buffers (DMA straight from / to them), pageable ones (staged), ragged chunk sizes,
+    repeated calls on one handle, and the single-kernel path (PB2_D2H_CHUNKS=1) must all give the same bits."""
+    import ctypes
+    lib = pb.load_library()
+
+    def pinned(n):
+        ptr = ctypes.c_void_p()
+        assert lib.pb2_host_alloc(ctypes.byref(ptr), 8 * n) == 0
+        return ptr, np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_double)), shape=(n,))
+
+    for K in (1000, 259, 70):
+        p, Z, _ = C.trajectory(3, K)
+        B = make(p)
+        d0, v0 = B.residual_jacobian(Z)                      # pageable numpy buffers
+        assert np.abs(d0 - CP.residual(p, Z)).max() < RES_TOL and np.abs(v0 - CP.jacobian_values(p, Z)).max() < JAC_TOL
+        pz, Zp = pinned(Z.size)
+        pd, dp = pinned(B.dim)
+        pv, vp = pinned(B.nnz_jac)
+        for rep in range(3):
+            Zr = Z + 1e-3 * rep
+            Zp[:] = Zr.reshape(-1, order="F")
+            dp[:] = np.nan
+            vp[:] = np.nan
+            assert lib.pb2_residual_jacobian(B._h, pz, pd, pv, 0) == 0
+            dr, vr = B.residual_jacobian(np.asfortranarray(Zr))
+            assert np.array_equal(dp, dr) and np.array_equal(vp, vr)
+        monkeypatch.setenv("PB2_D2H_CHUNKS", "1")
+        d1, v1 = B.residual_jacobian(np.asfortranarray(Z + 2e-3))
+        monkeypatch.delenv("PB2_D2H_CHUNKS")
+        assert np.array_equal(d1, dp) and np.array_equal(v1, vp)
+        B.close()
+        for q in (pz, pd, pv):
+            lib.pb2_host_free(q)
+
+
+@pytest.mark.parametrize("kind,b,m", [("density", 9, 2), ("density", 4, 1), ("density", 16, 3), ("density", 5, 0),
+                                      ("ket", 6, 2), ("ket", 16, 3), ("ket", 2, 1), ("ket", 8, 6),
+                                      ("unitary", 6, 2), ("unitary", 4, 3), ("unitary", 8, 4), ("unitary", 12, 1)])
+def test_tensor_core_hessian_shapes(kind, b, m, monkeypatch):
+    """Row a8 on the tensor cores for general generators (knot_dmmah.cuh): forward tiles (state, first- and
+    second-order jets) and adjoint tiles with the TRANSPOSED generator -- no symmetry assumed (density generators
+    have none).  Odd / padded sizes, m = 0, tiles shared by several column kinds; against the oracle, and against
+    the jet kernel the same handle runs with PB2_NO_DMMAH=1."""
+    p, Z, mu = _random_problem(kind, b, m, 9, seed=100 * b + m + 7)
+    B = make(p, "dmma")
+    assert B.hessian_algorithm == "dmmah"
+    h = B.hessian_values(Z, mu)
+    ho = KN.hessian_values(p, Z, mu)
+    assert np.abs(h - ho).max() < HESS_RTOL * max(1.0, np.abs(ho).max())
+    assert np.array_equal(h, B.hessian_values(Z, mu))                      # fixed summation order
+    monkeypatch.setenv("PB2_NO_DMMAH", "1")
+    Bj = make(p, "dmma")
+    assert Bj.hessian_algorithm == "generic"
+    hj = Bj.hessian_values(Z, mu)
+    assert np.abs(h - hj).max() < 1e-10 * max(1.0, np.abs(ho).max())
+    B.close()
+    Bj.close()
+
+
+def test_tensor_core_hessian_substeps_nan_and_full_size(monkeypatch):
+    """Data-dependent Taylor sub-steps per knot, NaN inputs confined to their knot, C2 / C4 at BASELINE sizes
+    against the C++ port on every knot, and the device-pointer entry point."""
+    import torch
+    p, Z, mu = C.trajectory(2, 12)
+    Z[p.dt_off, :] = np.geomspace(1e-6, 6.0, p.K)
+    B = make(p)
+    h = B.hessian_values(Z, mu)
+    ho = KN.hessian_values(p, Z, mu)
+    assert np.abs(h - ho).max() < 1e-8 * max(1.0, np.abs(ho).max())
+    Z2 = Z.copy(order="F")
+    Z2[p.u_off + 1, 4] = np.nan
+    h2 = B.hessian_values(Z2, mu).reshape(p.K - 1, -1)
+    assert np.isnan(h2[4]).all()
+    ok = [k for k in range(p.K - 1) if k != 4]
+    assert np.array_equal(h2[ok], h.reshape(p.K - 1, -1)[ok])
+    B.close()
+    for cfg in (2, 4):
+        p, Z, mu = C.trajectory(cfg)
+        B = make(p)
+        h = B.hessian_values(Z, mu)
+        hc = CP.hessian_values(p, Z, mu)
+        assert np.abs(h - hc).max() < HESS_RTOL * max(1.0, np.abs(hc).max())
+        dZ = torch.from_numpy(np.ascontiguousarray(Z.reshape(-1, order="F"))).cuda()
+        dmu = torch.from_numpy(mu).cuda()
+        dh = torch.zeros(B.nnz_hess, dtype=torch.float64, device="cuda")
+        B.hessian_device(dZ, dmu, dh, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(dh.cpu().numpy(), h)
+        B.close()
