@@ -56,8 +56,10 @@ struct DmmahParams {
 
 constexpr int kDmmahMaxWarps = 12;
 
+// two knots' CTAs per SM for the 8 x 8 variants: one CTA's per-knot prologue (dependent global loads of dt, u, x, mu)
+// runs under the other one's Horner steps
 template <int NT, int W>
-__global__ void __launch_bounds__(32 * kDmmahMaxWarps, 1) knot_dmmah_kernel(DmmahParams p) {
+__global__ void __launch_bounds__(32 * kDmmahMaxWarps, NT == 1 ? 2 : 1) knot_dmmah_kernel(DmmahParams p) {
   constexpr int KT = 2 * NT, Bp = 8 * NT, FR = KT * NT * 32, W2 = 2 * W;
   extern __shared__ __align__(16) double hs[];
   if (p.mem_n > 1) {
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(32 * kDmmahMaxWarps, 1) knot_dmmah_kernel(Dmma
   const uint32_t a_sY = smem_u32(hs + p.o_sY), ybytes = 8u * (uint32_t)p.ybuf;
   const uint32_t ypub = a_sY + 8u * (uint32_t)((pcol < 0 ? 0 : pcol) * Bp + 2 * q);
   const bool tile_cpl = __any_sync(0xffffffffu, kind == 2 || kind == 3 || kind == 5);
+  const bool tile_two = __any_sync(0xffffffffu, kind == 3 && pi != pj);   // some lane of this tile has two parents
 
   double ev[KT][W2];
   uint32_t yrd[KT][W2];
@@ -214,6 +217,11 @@ __global__ void __launch_bounds__(32 * kDmmahMaxWarps, 1) knot_dmmah_kernel(Dmma
       for (int kq = M - 1; kq >= 0; --kq) {
         const double ck = hs[p.o_sC + kq];
         const uint32_t par = (step & 1u) * ybytes;
+        // a_k B before the barrier; the coupling sum as two short chains (the FP64 pipe is shared with the other
+        // warps' DMMAs and in order: every dependent level costs a pass through its queue)
+        double cb[KT];
+#pragma unroll
+        for (int i = 0; i < KT; ++i) cb[i] = ck * base[i];
         if (pcol >= 0) {
 #pragma unroll
           for (int i = 0; i < KT; ++i) sts_f64<0>(ypub + par + 8u * (8 * (i >> 1) + (i & 1)), t[i]);
@@ -223,10 +231,16 @@ __global__ void __launch_bounds__(32 * kDmmahMaxWarps, 1) knot_dmmah_kernel(Dmma
         double d[NT][2];
 #pragma unroll
         for (int i = 0; i < KT; ++i) {
-          double v = ck * base[i];
+          double v = cb[i];
           if (tile_cpl) {
 #pragma unroll
-            for (int ww = 0; ww < W2; ++ww) v = fma(ev[i][ww], lds_f64<0>(yrd[i][ww] + par), v);
+            for (int ww = 0; ww < W; ++ww) v = fma(ev[i][ww], lds_f64<0>(yrd[i][ww] + par), v);
+            if (tile_two) {      // second parent as its own short chain (warp-uniform: most tiles have none)
+              double v2 = ev[i][W] * lds_f64<0>(yrd[i][W] + par);
+#pragma unroll
+              for (int ww = W + 1; ww < W2; ++ww) v2 = fma(ev[i][ww], lds_f64<0>(yrd[i][ww] + par), v2);
+              v += v2;
+            }
           }
           d[i >> 1][i & 1] = v;
         }
