@@ -175,17 +175,6 @@ __device__ __forceinline__ void horner_step(double (&t)[2 * NT], const double (&
                                             bool in_x, bool pub, bool cpl, int bar_x, int nx, unsigned diag) {
   constexpr int KT = 2 * NT, YB = KT * 32 * 8;
   PB2_STEP_STAMP(0);
-  // a_k B before the exchange barrier: one dependent FP64 level less behind it
-  double ck = 0.0;
-  if (MODE != 2) ck = lds_f64<0>(ck_addr);
-  double cb[KT];
-#pragma unroll
-  for (int i = 0; i < KT; ++i) {
-    double v = 0.0;
-    if (MODE == 1) v = ck * base[i];
-    if (MODE == 0 && ((diag >> i) & 1u)) v = ck;
-    cb[i] = v;
-  }
   if (in_x) {
     if (pub) {
 #pragma unroll
@@ -201,12 +190,16 @@ __device__ __forceinline__ void horner_step(double (&t)[2 * NT], const double (&
 #pragma unroll
       for (int ww = 0; ww < W; ++ww) y[i][ww] = lds_f64<PAR * YB>(yrd[i][ww]);
   }
+  double ck = 0.0;
+  if (MODE != 2) ck = lds_f64<0>(ck_addr);
   // every additive term goes into the accumulators BEFORE the products (see knot_u8.cuh, u8_mma_acc:
   // an FP64 CUDA-core instruction after the DMMAs would queue behind the other warps' tensor work)
   double d[NT][2];
 #pragma unroll
   for (int i = 0; i < KT; ++i) {
-    double v = cb[i];
+    double v = 0.0;
+    if (MODE == 1) v = ck * base[i];
+    if (MODE == 0 && ((diag >> i) & 1u)) v = ck;
     if (cpl) {
 #pragma unroll
       for (int ww = 0; ww < W; ++ww) v = fma(ev[i][ww], y[i][ww], v);

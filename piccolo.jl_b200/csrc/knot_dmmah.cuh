@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(32 * kDmmahMaxWarps, NT == 1 ? 2 : 1) knot_dmm
   const uint32_t a_sY = smem_u32(hs + p.o_sY), ybytes = 8u * (uint32_t)p.ybuf;
   const uint32_t ypub = a_sY + 8u * (uint32_t)((pcol < 0 ? 0 : pcol) * Bp + 2 * q);
   const bool tile_cpl = __any_sync(0xffffffffu, kind == 2 || kind == 3 || kind == 5);
-  const bool tile_two = __any_sync(0xffffffffu, kind == 3 && pi != pj);   // some lane of this tile has two parents
 
   double ev[KT][W2];
   uint32_t yrd[KT][W2];
@@ -217,8 +216,8 @@ __global__ void __launch_bounds__(32 * kDmmahMaxWarps, NT == 1 ? 2 : 1) knot_dmm
       for (int kq = M - 1; kq >= 0; --kq) {
         const double ck = hs[p.o_sC + kq];
         const uint32_t par = (step & 1u) * ybytes;
-        // a_k B before the barrier; the coupling sum as two short chains (the FP64 pipe is shared with the other
-        // warps' DMMAs and in order: every dependent level costs a pass through its queue)
+        // a_k B before the barrier.  (Splitting the coupling sum into two shorter chains, or skipping the second
+        // parent's terms on tiles without mixed second-order lanes, was measured: no gain / 8 % slower on C4.)
         double cb[KT];
 #pragma unroll
         for (int i = 0; i < KT; ++i) cb[i] = ck * base[i];
@@ -234,13 +233,7 @@ __global__ void __launch_bounds__(32 * kDmmahMaxWarps, NT == 1 ? 2 : 1) knot_dmm
           double v = cb[i];
           if (tile_cpl) {
 #pragma unroll
-            for (int ww = 0; ww < W; ++ww) v = fma(ev[i][ww], lds_f64<0>(yrd[i][ww] + par), v);
-            if (tile_two) {      // second parent as its own short chain (warp-uniform: most tiles have none)
-              double v2 = ev[i][W] * lds_f64<0>(yrd[i][W] + par);
-#pragma unroll
-              for (int ww = W + 1; ww < W2; ++ww) v2 = fma(ev[i][ww], lds_f64<0>(yrd[i][ww] + par), v2);
-              v += v2;
-            }
+            for (int ww = 0; ww < W2; ++ww) v = fma(ev[i][ww], lds_f64<0>(yrd[i][ww] + par), v);
           }
           d[i >> 1][i & 1] = v;
         }
