@@ -1189,7 +1189,15 @@ int pb2_residual_jacobian(pb2_handle* h, const double* Z, double* delta, double*
           h->nk_sub = k1 - k0;
           rc = launch_resjac(h, h->dZ + k0 * D, nullptr, h->dComp + k0 * cs, h->stream, 1, 0, nullptr, 0, 1);
           h->nk_sub = -1;
-          if (rc) return rc;
+          if (rc) {
+            // earlier chunks are in flight and read / write the caller's buffers: drain them before reporting
+            const std::string msg = g_err;
+            cudaStreamSynchronize(h->s_in);
+            cudaStreamSynchronize(h->stream);
+            cudaStreamSynchronize(h->s_out);
+            cudaGetLastError();
+            return fail(rc, msg);
+          }
           PB2_CUDA(cudaEventRecord(h->k_ev[c], h->stream));
           PB2_CUDA(cudaStreamWaitEvent(h->s_out, h->k_ev[c], 0));
           PB2_CUDA(cudaMemcpyAsync(h->hComp + k0 * cs, h->dComp + k0 * cs, (size_t)(k1 - k0) * cs * sizeof(double),
@@ -1376,7 +1384,7 @@ void pb2_batch_destroy(pb2_batch* b) {
 }
 
 int pb2_batch_create(const pb2_desc* descs, int32_t n, pb2_batch** out) {
-  if (!descs || !out || n < 1) return fail(PB2_EINVAL, "pb2_batch_create: bad argument");
+  if (!descs || !out || n < 1 || n > 65535) return fail(PB2_EINVAL, "pb2_batch_create: bad argument (1 .. 65535 members)");
   *out = nullptr;
   const pb2_desc& d0 = descs[0];
   for (int i = 1; i < n; ++i) {
