@@ -55,11 +55,13 @@ struct DmmahParams {
 };
 
 constexpr int kDmmahMaxWarps = 12;
+// the 3-qubit unitary shape (15 forward + 5 adjoint tiles) fits as 20 warps when the couplings are one entry wide
+__host__ __device__ constexpr int dmmah_max_warps(int NT, int W) { return (NT == 2 && W == 1) ? 20 : kDmmahMaxWarps; }
 
 // two knots' CTAs per SM for the 8 x 8 variants: one CTA's per-knot prologue (dependent global loads of dt, u, x, mu)
 // runs under the other one's Horner steps
 template <int NT, int W>
-__global__ void __launch_bounds__(32 * kDmmahMaxWarps, NT == 1 ? 2 : 1) knot_dmmah_kernel(DmmahParams p) {
+__global__ void __launch_bounds__(32 * dmmah_max_warps(NT, W), NT == 1 ? 2 : 1) knot_dmmah_kernel(DmmahParams p) {
   constexpr int KT = 2 * NT, Bp = 8 * NT, FR = KT * NT * 32, W2 = 2 * W;
   extern __shared__ __align__(16) double hs[];
   if (p.mem_n > 1) {
@@ -335,7 +337,6 @@ inline DmmahPlan dmmah_plan(int b, int n_b, int m, const double* G0, const doubl
   const int KT = 2 * pl.NT, NT = pl.NT, Bp = pl.Bp, npair = m * (m + 1) / 2;
   pl.tiles_f = (n_b * (1 + m + npair) + 7) / 8;
   pl.tiles_a = (n_b * (1 + m) + 7) / 8;
-  if (pl.tiles_f + pl.tiles_a > kDmmahMaxWarps || npair + m + 1 > 32 * (pl.tiles_f + pl.tiles_a)) return pl;
   auto at = [&](int mat, int r, int c) -> double {
     if (r >= b || c >= b) return 0.0;
     const double* A = mat == 0 ? G0 : Gj + (size_t)(mat - 1) * b * b;
@@ -354,6 +355,7 @@ inline DmmahPlan dmmah_plan(int b, int n_b, int m, const double* G0, const doubl
   if (W > 4) return pl;
   W = W <= 1 ? 1 : (W <= 2 ? 2 : 4);
   pl.W = W;
+  if (pl.tiles_f + pl.tiles_a > dmmah_max_warps(pl.NT, W) || npair + m + 1 > 32 * (pl.tiles_f + pl.tiles_a)) return pl;
   const size_t FR = (size_t)KT * NT * 32;
   pl.gfrag.assign((m + 1) * FR, 0.0);
   pl.gfragT.assign((m + 1) * FR, 0.0);

@@ -161,6 +161,7 @@ struct pb2_handle {
   double *dHGfrag = nullptr, *dHGfragT = nullptr, *dHNorms = nullptr;
   pb2::EllEntry *dHEll = nullptr, *dHEllT = nullptr;
   int dmmah = 1;               // PB2_NO_DMMAH=1: Hessian through the jet kernel
+  int hess_prefer_dmmah = 0;   // PB2_HESS_DMMAH=1: the general tensor-core Hessian also for the 3-qubit shape
   double* dNorms = nullptr;
   double* dTab = nullptr;
   double *dComp = nullptr, *hComp = nullptr;   // compact records: device buffer and pinned landing zone
@@ -511,7 +512,8 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
     p.mem_n = bl->n; p.x_offs = bl->x_offs; p.G0 = bl->G0; p.Gj = bl->Gj;
     p.mem_G0 = bl->mem_G0; p.mem_Gj = bl->mem_Gj; p.mem_delta = bl->mem_delta; p.mem_hess = bl->mem_hess;
   }
-  if (!bl && h->u8h_ok && ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)dmu % 16 == 0) && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
+  if (!bl && h->u8h_ok && !(h->hplan.ok && h->hess_prefer_dmmah) && ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)dmu % 16 == 0) &&
+      (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
     // 3-qubit unitary shape, anti-symmetric generators: tensor-core Hessian (forward + adjoint jets)
     pb2::U8hParams q{};
     q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
@@ -745,6 +747,7 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     // the Lagrangian Hessian on the tensor cores too (the 3-qubit shape has its own kernel; time-dependent handles
     // have no Hessian)
     h->dmmah = std::getenv("PB2_NO_DMMAH") ? 0 : 1;
+    h->hess_prefer_dmmah = std::getenv("PB2_HESS_DMMAH") ? std::atoi(std::getenv("PB2_HESS_DMMAH")) : 0;
     if (h->dmmah && !d.time_dependent) h->hplan = pb2::dmmah_plan(d.b, d.n_b, d.m, h->G0.data(), h->Gj.data());
     if (h->hplan.ok) {
       const pb2::DmmahPlan& hp = h->hplan;
@@ -906,7 +909,7 @@ int64_t pb2_nnz_hess(const pb2_handle* h) { return h ? (int64_t)h->nnz_hess_knot
 int32_t pb2_hessian_algorithm(const pb2_handle* h) {
   if (!h) return -1;
   if (h->d.time_dependent) return 0;
-  if (h->u8h_ok && (h->d.D % 2 == 0) && (h->d.x_off % 2 == 0)) return 3;
+  if (h->u8h_ok && !(h->hplan.ok && h->hess_prefer_dmmah) && (h->d.D % 2 == 0) && (h->d.x_off % 2 == 0)) return 3;
   return h->hplan.ok ? 2 : 1;
 }
 

@@ -1690,3 +1690,22 @@ def test_tensor_core_hessian_substeps_nan_and_full_size(monkeypatch):
         torch.cuda.synchronize()
         assert np.array_equal(dh.cpu().numpy(), h)
         B.close()
+
+
+def test_tensor_core_hessian_twenty_warps(monkeypatch):
+    """The 3-qubit unitary shape through the GENERAL tensor-core Hessian (15 forward + 5 adjoint tiles = 20 warps per
+    knot; PB2_HESS_DMMAH=1 prefers it over knot_u8h, which is faster and stays the default): against the oracle and
+    against knot_u8h."""
+    p, Z, mu = C.trajectory(3, 23)
+    B = make(p)
+    assert B.hessian_algorithm == "u8h"
+    h0 = B.hessian_values(Z, mu)
+    B.close()
+    monkeypatch.setenv("PB2_HESS_DMMAH", "1")
+    B = make(p)
+    assert B.hessian_algorithm == "dmmah"
+    h = B.hessian_values(Z, mu)
+    ho = KN.hessian_values(p, Z, mu)
+    assert np.abs(h - ho).max() < HESS_RTOL * max(1.0, np.abs(ho).max())
+    assert np.abs(h - h0).max() < 1e-10 * max(1.0, np.abs(ho).max())
+    B.close()
