@@ -26,6 +26,7 @@
 #include "knot_u8.cuh"
 #include "knot_u8h.cuh"
 #include "knot_dmmah.cuh"
+#include "knot_dmmaq.cuh"
 #include "knot_aux.cuh"
 #include "knot_objective.cuh"
 #include "knot_rollout.cuh"
@@ -162,6 +163,8 @@ struct pb2_handle {
   pb2::EllEntry *dHEll = nullptr, *dHEllT = nullptr;
   int dmmah = 1;               // PB2_NO_DMMAH=1: Hessian through the jet kernel
   int hess_prefer_dmmah = 0;   // PB2_HESS_DMMAH=1: the general tensor-core Hessian also for the 3-qubit shape
+  int dmmaq = 1;               // residual + Jacobian of the general shapes as one small CTA per knot (PB2_DMMAQ=0:
+                               // the persistent pipelined kernel knot_dmma)
   double* dNorms = nullptr;
   double* dTab = nullptr;
   double *dComp = nullptr, *hComp = nullptr;   // compact records: device buffer and pinned landing zone
@@ -449,6 +452,35 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
     if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("u8 resjac launch: ") + cudaGetErrorString(e));
   } else if (compact) {
     return fail(PB2_EINVAL, "compact records are only produced by the 3-qubit unitary kernel with aligned pointers");
+  } else if (h->alg == PB2_ALG_DMMA && h->dmmaq) {
+    // one small CTA per knot, several resident per SM (knot_dmmaq.cuh)
+    const bool jets = djac != nullptr;
+    const pb2::DmmaPlan& pl = h->plan;
+    pb2::DmmaqParams q{};
+    q.b = p.b; q.n_b = p.n_b; q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
+    q.nnz_jac = p.nnz_jac; q.max_sub = 4096; q.nk = (int)h->nk();
+    q.ncT = jets ? pl.ncT : 0; q.iso = pl.iso; q.m_jets = jets ? p.m : 0;
+    q.tiles = jets ? pl.tiles_full : pl.tiles_res;
+    q.Gfrag = h->dGfrag; q.ell = h->dEll; q.norms = h->dNorms;
+    q.Z = dZ; q.delta = ddelta; q.jac = djac;
+    if (bl) {
+      q.mem_n = bl->n; q.x_offs = bl->x_offs; q.Gfrag = bl->gfrag; q.ell = bl->ell; q.norms = bl->norms;
+      q.mem_gfrag = bl->mem_gfrag; q.mem_ell = bl->mem_ell; q.mem_norms = bl->mem_norms;
+      q.mem_delta = bl->mem_delta; q.mem_jac = bl->mem_jac;
+    }
+    const size_t smem = pb2::dmmaq_layout(q, pl.NT);
+    const int threads = 32 * q.tiles;
+    pb2::DmmaqKernel kern = pb2::dmmaq_kernel(pl.NT, pl.W);
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
+      cudaGetLastError();
+      occ = 1;
+    }
+    const int n_mem = bl ? bl->n : 1;
+    const int blocks = (int)std::min<int64_t>(q.nk, std::max(1, h->n_sm * occ / n_mem));
+    kern<<<dim3(blocks, n_mem), threads, smem, st>>>(q);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("dmmaq resjac launch: ") + cudaGetErrorString(e));
   } else if (h->alg == PB2_ALG_DMMA) {
     // residual-only calls carry just the state columns; anything with a Jacobian carries the
     // propagator columns and one jet per drive as well
@@ -748,6 +780,8 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     // have no Hessian)
     h->dmmah = std::getenv("PB2_NO_DMMAH") ? 0 : 1;
     h->hess_prefer_dmmah = std::getenv("PB2_HESS_DMMAH") ? std::atoi(std::getenv("PB2_HESS_DMMAH")) : 0;
+    h->dmmaq = std::getenv("PB2_DMMAQ") ? std::atoi(std::getenv("PB2_DMMAQ")) : 1;
+    if (h->dmmaq) PB2_CUDA_H(raise_dynamic_smem(pb2::dmmaq_kernel(h->plan.NT, h->plan.W)));
     if (h->dmmah && !d.time_dependent) h->hplan = pb2::dmmah_plan(d.b, d.n_b, d.m, h->G0.data(), h->Gj.data());
     if (h->hplan.ok) {
       const pb2::DmmahPlan& hp = h->hplan;

@@ -392,24 +392,30 @@ def _random_problem(kind, b, m, K, seed):
 @pytest.mark.parametrize("kind,b,m", [("density", 9, 2), ("density", 4, 1), ("density", 16, 3),
                                       ("density", 5, 0), ("ket", 6, 2), ("ket", 16, 3), ("ket", 2, 1),
                                       ("unitary", 6, 2), ("unitary", 12, 1), ("unitary", 16, 6)])
-def test_tensor_core_path_shapes(kind, b, m):
+def test_tensor_core_path_shapes(kind, b, m, monkeypatch):
     """Odd / padded generator sizes, m = 0, mixed tiles (propagator, state and jet columns sharing
-    one 8-column tile), the widest supported problem (8 tiles)."""
+    one 8-column tile), the widest supported problem (8 tiles) -- through the default small-CTA kernel (knot_dmmaq)
+    and through the persistent pipelined one (knot_dmma, PB2_DMMAQ=0)."""
     p, Z, mu = _random_problem(kind, b, m, 9, seed=100 * b + m)
-    B = make(p, "dmma")
-    assert B.algorithm == "dmma"
-    d, v = B.residual_jacobian(Z)
-    assert np.abs(d - KN.residual(p, Z)).max() < 1e-11
-    assert np.abs(v - KN.jacobian_values(p, Z)).max() < 1e-10
-    d2 = np.empty(B.dim)
-    B.evaluate_(d2, Z)                       # residual-only launch carries no jets
-    assert np.abs(d2 - d).max() < 1e-13
-    assert np.array_equal(v, B.jacobian_values(Z))
-    B.close()
+    for env in (None, "0"):
+        if env is not None:
+            monkeypatch.setenv("PB2_DMMAQ", env)
+        B = make(p, "dmma")
+        assert B.algorithm == "dmma"
+        d, v = B.residual_jacobian(Z)
+        assert np.abs(d - KN.residual(p, Z)).max() < 1e-11
+        assert np.abs(v - KN.jacobian_values(p, Z)).max() < 1e-10
+        d2 = np.empty(B.dim)
+        B.evaluate_(d2, Z)                       # residual-only launch carries no jets
+        assert np.abs(d2 - d).max() < 1e-13
+        assert np.array_equal(v, B.jacobian_values(Z))
+        B.close()
 
 
-def test_tensor_core_path_substeps_and_limits():
+@pytest.mark.parametrize("dmmaq", ["1", "0"])
+def test_tensor_core_path_substeps_and_limits(dmmaq, monkeypatch):
     """||dt G|| from tiny to ~60: the number of Taylor sub-steps is data dependent per knot."""
+    monkeypatch.setenv("PB2_DMMAQ", dmmaq)
     p, Z, mu = C.trajectory(2, 12)
     Z[p.dt_off, :] = np.geomspace(1e-6, 6.0, p.K)
     B = make(p, "dmma")
