@@ -126,7 +126,10 @@ __device__ __forceinline__ void u8q_step_B(double (&tE)[4], double (&t)[2][4], c
 }
 
 // NS = knots (slots) per CTA: 4 -> 256 threads, two CTAs per SM, slot s on sub-partition s (6 tiles each);
-//                             2 -> 128 threads, four CTAs per SM, warps A0 B0 A1 B1 on sub-partitions 0..3 (3 tiles each).
+//                             2 -> 128 threads, four CTAs per SM, warps A0 B0 A1 B1 on sub-partitions 0..3 (3 tiles each);
+//                             1 -> 64 threads, eight CTAs per SM: every knot its own CTA, so all of an SM's 6.75 knots
+//                                  (C3) are resident at once and the scheduler refills a slot the moment ONE knot
+//                                  retires (measured: C3 8.53 -> 7.4 us per callback, C5 56.7 -> 54.3 us; the default).
 template <bool UNIT, int NS>
 __global__ void __launch_bounds__(64 * NS, 8 / NS) knot_u8q_kernel(const __grid_constant__ U8qParams p) {
   extern __shared__ __align__(16) double u8q_smem[];
@@ -614,6 +617,7 @@ inline std::vector<double> u8q_tables(const DmmaPlan& pl, int m, const double* t
 
 inline auto u8q_kernel(bool unit, int ns) -> void (*)(const U8qParams) {
   if (ns == 2) return unit ? knot_u8q_kernel<true, 2> : knot_u8q_kernel<false, 2>;
+  if (ns == 1) return unit ? knot_u8q_kernel<true, 1> : knot_u8q_kernel<false, 1>;
   return unit ? knot_u8q_kernel<true, 4> : knot_u8q_kernel<false, 4>;
 }
 

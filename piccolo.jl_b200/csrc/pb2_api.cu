@@ -191,7 +191,7 @@ struct pb2_handle {
   int u8s = 0;             // first single-round draft (whole-knot slots), kept for A/B measurements (PB2_U8S=1)
   int u8p = 1;             // single-round kernel for <= 7 knots per SM (knot_u8p.cuh); PB2_U8P=0 disables it
   int u8q = 2;             // small-CTA kernel (knot_u8q.cuh): 2 = every size, 1 = at most 7 knots per SM, 0 = off (PB2_U8Q)
-  int u8q_ns = 2;          // knots per CTA: 4 (two CTAs per SM) or 2 (four CTAs per SM); PB2_U8Q_NS
+  int u8q_ns = 1;          // knots per CTA: 1 (eight 64-thread CTAs per SM, the default), 2 or 4; PB2_U8Q_NS
   int u8q_space = 0;       // minimum spacing (cycles) of the product phases of CTAs sharing an SM; PB2_U8Q_SPACE
   unsigned long long* dSmClock = nullptr;
   unsigned long long* dSyncWords = nullptr;   // [0] ticket, [1] exchange epoch (knot_u8q.cuh, in-kernel step barrier)
@@ -289,7 +289,21 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
     p.mem_n = bl->n; p.x_offs = bl->x_offs; p.G0 = bl->G0; p.Gj = bl->Gj;
     p.mem_G0 = bl->mem_G0; p.mem_Gj = bl->mem_Gj; p.mem_delta = bl->mem_delta; p.mem_jac = bl->mem_jac;
   }
-  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8q && !h->u8s && djac && aligned16 && (p.D % 2 == 0) &&
+  // knots per CTA of the small-CTA 3-qubit kernel: the configured count, or the next larger one whose CTA still holds the
+  // table blob and its knot slots (the blob is per CTA: long knot columns leave room for fewer, larger CTAs); 0 = the
+  // column does not fit at all and the older kernels below take the call
+  int u8q_ns = 0;
+  if (h->u8p_ok && h->u8q) {
+    pb2::U8qParams probe{};
+    probe.m = p.m; probe.zlen = p.D + p.x_off + 128; probe.n_peers = n_peers ? n_peers : (compact ? 8 : 0);
+    probe.cstride = (p.m + 3) * 128;
+    for (int ns = h->u8q_ns; ns <= 4 && !u8q_ns; ns *= 2)
+      if (pb2::u8q_layout(probe, ns) <= kSmemLimit / (size_t)(8 / ns)) u8q_ns = ns;
+  }
+  // (when even four knots per CTA do not fit, the column is too long for any of the slab-staging 3-qubit kernels: the
+  // general kernel, which reads the trajectory straight from global memory, takes the call)
+  const bool slab_fits = !(h->u8p_ok && h->u8q) || u8q_ns != 0;
+  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8q && u8q_ns && !h->u8s && djac && aligned16 && (p.D % 2 == 0) &&
       (p.x_off % 2 == 0) && (n_peers == 0 || !std::getenv("PB2_U8Q_NO_PEERS")) &&
       (h->u8q >= 2 || h->nk() <= (int64_t)7 * h->n_sm)) {
     // two 256-thread CTAs per SM, at most four knots each: one CTA's prologue and tail run underneath the
@@ -313,7 +327,7 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
 #ifdef PB2_TRACE
     q.trace = h->dTrace3; q.trace_id = (h->trace_launch++) % 64;
 #endif
-    const int ns = h->u8q_ns, cps = 8 / ns;   // knots per CTA, CTAs per SM
+    const int ns = u8q_ns, cps = 8 / ns;   // knots per CTA, CTAs per SM
     q.space = h->u8q_space; q.sm_clock = h->dSmClock;
     if (const char* env = std::getenv("PB2_NOWAIT")) q.nowait = std::atoi(env);   // (measurement knob)
     q.pro = std::getenv("PB2_U8Q_PRO") ? std::atoi(std::getenv("PB2_U8Q_PRO")) : 3000;
@@ -345,7 +359,7 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
     h->launches++;
     return PB2_OK;
   }
-  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8p && !h->u8s && djac && aligned16 && (p.D % 2 == 0) &&
+  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8p && !h->u8s && djac && aligned16 && slab_fits && (p.D % 2 == 0) &&
       (p.x_off % 2 == 0) && n_peers == 0 && h->nk() <= (int64_t)pb2::kU8pSlots * h->n_sm) {
     // at most seven knots per SM: every knot of an SM in flight at once, propagator tiles first (knot_u8p.cuh)
     pb2::U8pParams q{};
@@ -378,7 +392,7 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
     h->launches++;
     return PB2_OK;
   }
-  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8s && djac && aligned16 && (p.D % 2 == 0) && (p.x_off % 2 == 0) &&
+  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8s && djac && aligned16 && slab_fits && (p.D % 2 == 0) && (p.x_off % 2 == 0) &&
       (p.m == 3 || p.m == 4) && !compact && n_peers == 0 &&
       h->nk() <= (int64_t)pb2::kU8sSlots * h->n_sm) {
     // at most seven knots per SM: single-round kernel, every knot of an SM in flight (EXPERIMENTAL, PB2_U8S=1)
@@ -408,7 +422,7 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
     if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, q);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("u8s resjac launch: ") + cudaGetErrorString(e));
-  } else if (h->alg == PB2_ALG_DMMA && h->u8_ok && djac && aligned16 && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
+  } else if (h->alg == PB2_ALG_DMMA && h->u8_ok && djac && aligned16 && slab_fits && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
     // the 3-qubit unitary shape: warp-specialised kernel (producer warp + (E,X) warp + jet warps)
     const pb2::DmmaPlan& pl = h->plan;
     pb2::U8Params q{};
@@ -544,8 +558,15 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
     p.mem_n = bl->n; p.x_offs = bl->x_offs; p.G0 = bl->G0; p.Gj = bl->Gj;
     p.mem_G0 = bl->mem_G0; p.mem_Gj = bl->mem_Gj; p.mem_delta = bl->mem_delta; p.mem_hess = bl->mem_hess;
   }
-  if (!bl && h->u8h_ok && !(h->hplan.ok && h->hess_prefer_dmmah) && ((uintptr_t)dZ % 16 == 0) && ((uintptr_t)dmu % 16 == 0) &&
-      (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
+  bool u8h_fits = false;
+  if (h->u8h_ok) {
+    pb2::U8hParams probe{};
+    probe.m = p.m; probe.zlen = p.D + p.x_off + 128; probe.nnz_hess = p.nnz_hess;
+    probe.ntiles = 2 + 2 * p.m + p.m * (p.m + 1) / 2; probe.ncw = (probe.ntiles + 1) / 2;
+    u8h_fits = pb2::u8h_layout(probe) <= kSmemLimit;
+  }
+  if (!bl && h->u8h_ok && u8h_fits && !(h->hplan.ok && h->hess_prefer_dmmah) && ((uintptr_t)dZ % 16 == 0) &&
+      ((uintptr_t)dmu % 16 == 0) && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
     // 3-qubit unitary shape, anti-symmetric generators: tensor-core Hessian (forward + adjoint jets)
     pb2::U8hParams q{};
     q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
@@ -825,7 +846,10 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     if (const char* env = std::getenv("PB2_U8S")) h->u8s = std::atoi(env);
     if (const char* env = std::getenv("PB2_U8P")) h->u8p = std::atoi(env);
     if (const char* env = std::getenv("PB2_U8Q")) h->u8q = std::atoi(env);
-    if (const char* env = std::getenv("PB2_U8Q_NS")) h->u8q_ns = std::atoi(env) == 2 ? 2 : 4;
+    if (const char* env = std::getenv("PB2_U8Q_NS")) {
+      const int v = std::atoi(env);
+      h->u8q_ns = (v == 1 || v == 2) ? v : 4;
+    }
     if (const char* env = std::getenv("PB2_U8Q_SPACE")) h->u8q_space = std::atoi(env);
     if (const char* env = std::getenv("PB2_EARLY_Z")) h->early_z = std::atoi(env);
     if (const char* env = std::getenv("PB2_PIPELINED")) h->pipelined = std::atoi(env);
@@ -843,7 +867,7 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
         PB2_CUDA_H(cudaMemcpy(h->dTablesP, blob.data(), blob.size() * sizeof(double), cudaMemcpyHostToDevice));
         PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8p_kernel(h->u8p_unit), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)kSmemLimit));
-        for (int ns : {2, 4}) {
+        for (int ns : {1, 2, 4}) {
           PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8q_kernel(h->u8p_unit, ns), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)(kSmemLimit * ns / 8)));
           PB2_CUDA_H(cudaFuncSetAttribute(pb2::u8q_kernel(h->u8p_unit, ns), cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -1056,6 +1080,13 @@ int pb2_hess_lagrangian_async(pb2_handle* h, const double* dZ, const double* dmu
 
 int64_t pb2_compact_stride(const pb2_handle* h) {
   if (!h || !(h->alg == PB2_ALG_DMMA && h->u8_ok) || (h->d.D % 2) || (h->d.x_off % 2) || h->d.time_dependent || h->d.dense_blocks) return 0;
+  if (h->u8p_ok && h->u8q) {
+    // a knot column too long for the slab-staging kernels (even with four knots per CTA) goes through the general
+    // kernel, which writes canonical arrays only
+    pb2::U8qParams probe{};
+    probe.m = h->d.m; probe.zlen = h->d.D + h->d.x_off + 128; probe.n_peers = 8; probe.cstride = (h->d.m + 3) * 128;
+    if (pb2::u8q_layout(probe, 4) > kSmemLimit / 2) return 0;
+  }
   return (int64_t)(h->d.m + 3) * 128;
 }
 

@@ -1715,3 +1715,29 @@ def test_tensor_core_hessian_twenty_warps(monkeypatch):
     assert np.abs(h - ho).max() < HESS_RTOL * max(1.0, np.abs(ho).max())
     assert np.abs(h - h0).max() < 1e-10 * max(1.0, np.abs(ho).max())
     B.close()
+
+
+def test_single_knot_ctas_and_long_knot_columns():
+    """knot_u8q runs one knot per 64-thread CTA by default (eight CTAs per SM).  A long knot column (extra
+    trajectory components after the controls) leaves no room for the per-CTA table blob next to the slab: the launch
+    then packs two / four knots per CTA instead -- same results; beyond that the general kernels take over."""
+    import dataclasses
+    p0, Z0, _ = C.trajectory(3, 40)
+    base = make(p0)
+    d0, v0 = base.residual_jacobian(Z0)
+    base.close()
+    for extra in (900, 1300, 2400):
+        p = dataclasses.replace(p0, D=p0.D + extra)
+        Z = np.zeros((p.D, p.K), order="F")
+        Z[:p0.D] = Z0
+        Z[p0.D:] = np.random.default_rng(extra).standard_normal((extra, p.K))
+        B = make(p)
+        d, v = B.residual_jacobian(Z)
+        if extra < 2000:
+            assert np.array_equal(d, d0) and np.array_equal(v, v0)
+        else:       # too long for any slab-staging kernel: the general kernels take the call (Hessian included)
+            assert np.abs(d - d0).max() < PATH_TOL and np.abs(v - v0).max() < PATH_TOL
+            mu = np.random.default_rng(1).standard_normal(p.dim)
+            ho = KN.hessian_values(p, Z, mu)
+            assert np.abs(B.hessian_values(Z, mu) - ho).max() < HESS_RTOL * max(1.0, np.abs(ho).max())
+        B.close()
