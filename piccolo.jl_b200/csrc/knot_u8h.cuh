@@ -28,7 +28,7 @@ namespace pb2 {
 
 struct U8hParams {
   int m, D, x_off, dt_off, u_off, nnz_hess, max_sub, nk, zlen;
-  int ntiles, ncw;       // tiles per knot, compute warps (= ceil(ntiles / 2))
+  int ntiles, ncw;       // tiles per knot, compute warps (forward tiles two per warp, then adjoint tiles two per warp)
   // shared-memory layout in doubles (u8h_layout)
   int o_norm, o_tab, o_slab, zpad, o_prep, o_xch, o_stage, o_mbar;
   const double* tables;  // [G fragments (m+1) 256 | norms (padded even) | theta | 1/k!], smem order
@@ -79,7 +79,7 @@ template <int W, int PAR>
 __device__ __forceinline__ void u8h_step(double (&t)[2][4], const double (&base)[2][4], const double (&A)[4][2],
                                          const double (&ev)[2][2][4][W], const uint32_t (&yad)[2][2][4][W],
                                          const uint32_t (&pub)[2], const int (&skip)[2], const double (&sgn)[2],
-                                         const bool (&act)[2], int s, uint32_t ck_addr, int nthreads) {
+                                         const bool (&act)[2], int s, uint32_t ck_addr, int bar, int nthreads) {
 #pragma unroll
   for (int a = 0; a < 2; ++a)
     if (pub[a]) {
@@ -87,7 +87,7 @@ __device__ __forceinline__ void u8h_step(double (&t)[2][4], const double (&base)
       for (int i = 0; i < 4; ++i) sts_f64<PAR * kU8hXchBytes>(pub[a] + i * 256, t[a][i]);
     }
   const double ck = lds_f64<0>(ck_addr);
-  bar_sync(1, nthreads);
+  bar_sync(bar, nthreads);
   double d[2][2][2];
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
@@ -127,11 +127,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 template <int W>
-__global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant__ U8hParams p) {
+__global__ void __launch_bounds__(384, 1) knot_u8h_kernel(const __grid_constant__ U8hParams p) {
   extern __shared__ __align__(16) double u8_smem[];
   const int lane = threadIdx.x & 31, wcta = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
-  const int m = p.m, ncw = p.ncw, nthr = 32 * ncw;
+  const int m = p.m, ncw = p.ncw;
   const int npair = m * (m + 1) / 2;
 
   const uint32_t a_cG = smem_u32(u8_smem);
@@ -268,8 +268,13 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
   double ev[2][2][4][W];
   uint32_t yad[2][2][4][W];
 #pragma unroll
+  // forward tiles (X, J_j, P_ij) and adjoint tiles (Mt, JA_j) never exchange anything: they live in separate warps
+  // and meet on separate named barriers, so the two recurrences drift apart and fill each other's barrier gaps
+  const int nf = 1 + m + m * (m + 1) / 2, nfw = (nf + 1) / 2, naw = ncw - nfw;
+  const bool adj = cw >= nfw;
+  const int bar = adj ? 2 : 1, nthr = 32 * (adj ? naw : nfw);
   for (int a = 0; a < 2; ++a) {
-    const int tix = 2 * cw + a;
+    const int tix = adj ? nf + 2 * (cw - nfw) + a : (2 * cw + a < nf ? 2 * cw + a : p.ntiles);
     sl[a] = tix < p.ntiles ? u8h_tile(tix, m) : U8hSlot{U8H_NONE, 0, 0};
     const int kind = sl[a].kind;
     act[a] = kind != U8H_NONE;
@@ -279,7 +284,9 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
     pub[a] = kind == U8H_X ? a_xch + lane_x : (kind == U8H_MT ? a_xch + 1024u + lane_x
              : (kind == U8H_J ? a_xch + 1024u * (uint32_t)(2 + sl[a].j) + lane_x : 0u));
     // coupling terms: (drive, source buffer, scale)
-    int drv[2] = {m, m}, src[2] = {0, 0};
+    // (unused terms carry a zero coefficient and read the tile's OWN group's state buffer: the other group may be in
+    // a different knot, and 0 * NaN of a poisoned knot must not leak into this one)
+    int drv[2] = {m, m}, src[2] = {adj ? 1 : 0, adj ? 1 : 0};
     double sc[2] = {0.0, 0.0};
     if (kind == U8H_J) { drv[0] = sl[a].j; src[0] = 0; sc[0] = 1.0; }
     if (kind == U8H_JA) { drv[0] = sl[a].j; src[0] = 1; sc[0] = -1.0; }
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
         if (sl[a].kind == U8H_MT) v = mu4[i4];
         base[a][i4] = v;
       }
-    bar_sync(1, nthr);   // exchange buffers free (readers of the previous knot are done)
+    bar_sync(bar, nthr);   // exchange buffers free (readers of the previous knot are done)
     U8_STAMP(2);
     for (int sub = 0; sub < n_sub; ++sub) {
       const double cM = lds_f64<0>(a_c + 8u * (uint32_t)M);
@@ -347,15 +354,15 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
           if (sub > 0) base[a][i4] = t[a][i4];
           t[a][i4] = cM * base[a][i4];
         }
-      if (sub > 0) bar_sync(1, nthr);
+      if (sub > 0) bar_sync(bar, nthr);
       // the structural zeros of the first sub-step (jets start from zero) are skipped only there
       int skp[2] = {sub == 0 ? skip[0] : 0, sub == 0 ? skip[1] : 0};
       int s = 0, kq = M - 1;
       for (; kq >= 1; kq -= 2, s += 2) {
-        u8h_step<W, 0>(t, base, A, ev, yad, pub, skp, sgn, act, s, a_c + 8u * kq, nthr);
-        u8h_step<W, 1>(t, base, A, ev, yad, pub, skp, sgn, act, s + 1, a_c + 8u * kq - 8u, nthr);
+        u8h_step<W, 0>(t, base, A, ev, yad, pub, skp, sgn, act, s, a_c + 8u * kq, bar, nthr);
+        u8h_step<W, 1>(t, base, A, ev, yad, pub, skp, sgn, act, s + 1, a_c + 8u * kq - 8u, bar, nthr);
       }
-      if (kq == 0) u8h_step<W, 0>(t, base, A, ev, yad, pub, skp, sgn, act, s, a_c, nthr);
+      if (kq == 0) u8h_step<W, 0>(t, base, A, ev, yad, pub, skp, sgn, act, s, a_c, bar, nthr);
     }
 
     // ---- final products and contractions ------------------------------------------------------------
@@ -369,7 +376,7 @@ __global__ void __launch_bounds__(352, 1) knot_u8h_kernel(const __grid_constant_
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) sts_f64<0>(pub[a] + fo + i4 * 256, t[a][i4]);
       }
-    bar_sync(1, nthr);
+    bar_sync(bar, nthr);
     double outv[2][4];     // tile-shaped results (adjoint tiles)
     double outs[2];        // scalar results (forward tiles)
 #pragma unroll

@@ -562,7 +562,7 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
   if (h->u8h_ok) {
     pb2::U8hParams probe{};
     probe.m = p.m; probe.zlen = p.D + p.x_off + 128; probe.nnz_hess = p.nnz_hess;
-    probe.ntiles = 2 + 2 * p.m + p.m * (p.m + 1) / 2; probe.ncw = (probe.ntiles + 1) / 2;
+    probe.ntiles = 2 + 2 * p.m + p.m * (p.m + 1) / 2; probe.ncw = (probe.ntiles + 1) / 2;   // (layout does not depend on it)
     u8h_fits = pb2::u8h_layout(probe) <= kSmemLimit;
   }
   if (!bl && h->u8h_ok && u8h_fits && !(h->hplan.ok && h->hess_prefer_dmmah) && ((uintptr_t)dZ % 16 == 0) &&
@@ -573,7 +573,8 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
     q.nnz_hess = p.nnz_hess; q.max_sub = 4096; q.nk = (int)h->nk();
     q.zlen = p.D + p.x_off + 128;
     q.ntiles = 2 + 2 * p.m + p.m * (p.m + 1) / 2;
-    q.ncw = (q.ntiles + 1) / 2;
+    // forward and adjoint tiles in separate warps, two tiles per warp
+    q.ncw = (1 + p.m + p.m * (p.m + 1) / 2 + 1) / 2 + (1 + p.m + 1) / 2;
     q.tables = h->dTables; q.ell = h->dEll;
     q.Z = dZ; q.mu = dmu; q.hess = dhess; q.trace = h->dTrace2;
     const size_t smem = pb2::u8h_layout(q);
