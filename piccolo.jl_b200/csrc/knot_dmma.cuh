@@ -543,6 +543,7 @@ __global__ void __launch_bounds__(dmma_max_threads(NT, W), 1) knot_dmma_kernel(D
 struct DmmaPlan {
   bool ok = false;
   int NT = 0, Bp = 0, W = 1, iso = 0, ncT = 0;
+  bool persistent_ok = false;   // knot_dmma_kernel (NT <= 2, n_b <= 8) can take the shape; knot_dmmaq takes all of them
   int tiles_full = 0, tiles_res = 0;
   std::vector<double> gfrag;
   std::vector<EllEntry> ell;
@@ -554,8 +555,9 @@ inline int dmma_perm(int kt, int q) { return 8 * (kt / 2) + 2 * q + (kt % 2); }
 // G0, Gj: host, column-major b x b.  allow_iso: the state uses the half (real-isomorphism) layout.
 inline DmmaPlan dmma_plan(int b, int n_b, int m, bool allow_iso, const double* G0, const double* Gj) {
   DmmaPlan pl;
-  if (b < 1 || b > 16 || n_b > 8) return pl;
-  pl.NT = b <= 8 ? 1 : 2;
+  if (b < 1 || b > 24 || n_b > 12) return pl;
+  pl.NT = b <= 8 ? 1 : (b <= 16 ? 2 : 3);
+  pl.persistent_ok = pl.NT <= 2 && n_b <= 8;
   pl.Bp = 8 * pl.NT;
   const int KT = 2 * pl.NT, NT = pl.NT, Bp = pl.Bp;
   auto at = [&](int mat, int r, int c) -> double {

@@ -1,4 +1,4 @@
-// Tensor-core Lagrangian Hessian for general generators with b <= 16.
+// Tensor-core Lagrangian Hessian for general generators with b <= 24.
 //
 // What it replaces: the Hessian of sum_k mu_k . delta_k that DirectTrajOpt's BilinearIntegrator hands to Ipopt's
 // eval_h (constructed at /root/reference/src/control/integrators.jl:35-95; `hessian_structure`, test/aqua.jl:6-9),
@@ -56,12 +56,14 @@ struct DmmahParams {
 
 constexpr int kDmmahMaxWarps = 12;
 // the 3-qubit unitary shape (15 forward + 5 adjoint tiles) fits as 20 warps when the couplings are one entry wide
+// ... and the widest variant (24 x 24 generators, four coupling entries per row) keeps 48 + 48 coupling values and
+// addresses per lane: compiled for 12 warps (170 registers) it spills into the step loop (ncu: long-scoreboard stalls,
+// 324 us for a qutrit-pair ket problem); compiled for 8 warps (255 registers) it does not (74 us).  Knots that need
+// 9 - 12 warps of that variant still take the spilling build, which beats the jet kernel.
 __host__ __device__ constexpr int dmmah_max_warps(int NT, int W) { return (NT == 2 && W == 1) ? 20 : kDmmahMaxWarps; }
 
-// two knots' CTAs per SM for the 8 x 8 variants: one CTA's per-knot prologue (dependent global loads of dt, u, x, mu)
-// runs under the other one's Horner steps
-template <int NT, int W>
-__global__ void __launch_bounds__(32 * dmmah_max_warps(NT, W), NT == 1 ? 2 : 1) knot_dmmah_kernel(DmmahParams p) {
+template <int NT, int W, int MAXW = dmmah_max_warps(NT, W)>
+__global__ void __launch_bounds__(32 * MAXW, NT == 1 ? 2 : 1) knot_dmmah_kernel(DmmahParams p) {
   constexpr int KT = 2 * NT, Bp = 8 * NT, FR = KT * NT * 32, W2 = 2 * W;
   extern __shared__ __align__(16) double hs[];
   if (p.mem_n > 1) {
@@ -331,8 +333,8 @@ struct DmmahPlan {
 // G0, Gj: host, column-major b x b
 inline DmmahPlan dmmah_plan(int b, int n_b, int m, const double* G0, const double* Gj) {
   DmmahPlan pl;
-  if (b < 1 || b > 16 || n_b < 1) return pl;
-  pl.NT = b <= 8 ? 1 : 2;
+  if (b < 1 || b > 24 || n_b < 1) return pl;
+  pl.NT = b <= 8 ? 1 : (b <= 16 ? 2 : 3);
   pl.Bp = 8 * pl.NT;
   const int KT = 2 * pl.NT, NT = pl.NT, Bp = pl.Bp, npair = m * (m + 1) / 2;
   pl.tiles_f = (n_b * (1 + m + npair) + 7) / 8;
@@ -404,7 +406,9 @@ inline size_t dmmah_layout(DmmahParams& q, int NT) {
 
 using DmmahKernel = void (*)(DmmahParams);
 
-inline DmmahKernel dmmah_kernel(int NT, int W) {
+inline DmmahKernel dmmah_kernel(int NT, int W, int warps) {
+  if (NT == 3 && W == 4 && warps <= 8) return knot_dmmah_kernel<3, 4, 8>;
+  if (NT == 3) return W == 1 ? knot_dmmah_kernel<3, 1> : (W == 2 ? knot_dmmah_kernel<3, 2> : knot_dmmah_kernel<3, 4>);
   if (NT == 1) return W == 1 ? knot_dmmah_kernel<1, 1> : (W == 2 ? knot_dmmah_kernel<1, 2> : knot_dmmah_kernel<1, 4>);
   return W == 1 ? knot_dmmah_kernel<2, 1> : (W == 2 ? knot_dmmah_kernel<2, 2> : knot_dmmah_kernel<2, 4>);
 }

@@ -1,4 +1,4 @@
-// Residual + Jacobian on the tensor cores for general generators with b <= 16, many small CTAs
+// Residual + Jacobian on the tensor cores for general generators with b <= 24, many small CTAs
 // (SURVEY.md section 8, rows a1-a3, a7).
 //
 // Same mathematics and the same tables as knot_dmma.cuh (the reference's BilinearIntegrator,
@@ -270,6 +270,7 @@ inline size_t dmmaq_layout(DmmaqParams& q, int NT) {
 using DmmaqKernel = void (*)(DmmaqParams);
 
 inline DmmaqKernel dmmaq_kernel(int NT, int W) {
+  if (NT == 3) return W == 1 ? knot_dmmaq_kernel<3, 1> : (W == 2 ? knot_dmmaq_kernel<3, 2> : knot_dmmaq_kernel<3, 4>);
   if (NT == 1) return W == 1 ? knot_dmmaq_kernel<1, 1> : (W == 2 ? knot_dmmaq_kernel<1, 2> : knot_dmmaq_kernel<1, 4>);
   return W == 1 ? knot_dmmaq_kernel<2, 1> : (W == 2 ? knot_dmmaq_kernel<2, 2> : knot_dmmaq_kernel<2, 4>);
 }

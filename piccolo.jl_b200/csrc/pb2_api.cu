@@ -158,7 +158,7 @@ struct pb2_handle {
   double *dG0 = nullptr, *dGj = nullptr;
   pb2::DmmaPlan plan;          // tensor-core path tables (host copy) and their device mirrors
   double* dGfrag = nullptr;
-  pb2::DmmahPlan hplan;        // tensor-core Hessian (general b <= 16): tables and their device mirrors
+  pb2::DmmahPlan hplan;        // tensor-core Hessian (general b <= 24): tables and their device mirrors
   double *dHGfrag = nullptr, *dHGfragT = nullptr, *dHNorms = nullptr;
   pb2::EllEntry *dHEll = nullptr, *dHEllT = nullptr;
   int dmmah = 1;               // PB2_NO_DMMAH=1: Hessian through the jet kernel
@@ -602,7 +602,7 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
     }
     const size_t smem = pb2::dmmah_layout(q, hp.NT);
     const int threads = 32 * (hp.tiles_f + hp.tiles_a);
-    pb2::DmmahKernel kern = pb2::dmmah_kernel(hp.NT, hp.W);
+    pb2::DmmahKernel kern = pb2::dmmah_kernel(hp.NT, hp.W, hp.tiles_f + hp.tiles_a);
     int occ = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
       cudaGetLastError();
@@ -747,7 +747,7 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
   if (d.algorithm == PB2_ALG_DMMA && !h->plan.ok) {
     delete h;
     return fail(PB2_EINVAL, "pb2_create: tensor-core path unsupported for this generator "
-                            "(needs b <= 16, <= 4 nonzeros per drive-generator row, <= 8 column tiles)");
+                            "(needs b <= 24, <= 4 nonzeros per drive-generator row, <= 8 column tiles)");
   }
   h->alg = h->plan.ok ? PB2_ALG_DMMA : PB2_ALG_GENERIC;
 
@@ -803,6 +803,7 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     h->dmmah = std::getenv("PB2_NO_DMMAH") ? 0 : 1;
     h->hess_prefer_dmmah = std::getenv("PB2_HESS_DMMAH") ? std::atoi(std::getenv("PB2_HESS_DMMAH")) : 0;
     h->dmmaq = std::getenv("PB2_DMMAQ") ? std::atoi(std::getenv("PB2_DMMAQ")) : 1;
+    if (!h->plan.persistent_ok) h->dmmaq = 1;   // 17 <= b <= 24 or more than 8 state columns: only the small-CTA kernel
     if (h->dmmaq) PB2_CUDA_H(raise_dynamic_smem(pb2::dmmaq_kernel(h->plan.NT, h->plan.W)));
     if (h->dmmah && !d.time_dependent) h->hplan = pb2::dmmah_plan(d.b, d.n_b, d.m, h->G0.data(), h->Gj.data());
     if (h->hplan.ok) {
@@ -818,7 +819,7 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
       PB2_CUDA_H(cudaMemcpy(h->dHEll, hp.ell.data(), he, cudaMemcpyHostToDevice));
       PB2_CUDA_H(cudaMemcpy(h->dHEllT, hp.ellT.data(), he, cudaMemcpyHostToDevice));
       PB2_CUDA_H(cudaMemcpy(h->dHNorms, hp.norms.data(), hp.norms.size() * sizeof(double), cudaMemcpyHostToDevice));
-      PB2_CUDA_H(raise_dynamic_smem(pb2::dmmah_kernel(hp.NT, hp.W)));
+      PB2_CUDA_H(raise_dynamic_smem(pb2::dmmah_kernel(hp.NT, hp.W, hp.tiles_f + hp.tiles_a)));
     }
     double invfact[pb2::kMaxDeg + 1];
     invfact[0] = 1.0;
@@ -836,8 +837,9 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
       PB2_CUDA_H(cudaMalloc(&h->dTables, tb.size() * sizeof(double)));
       PB2_CUDA_H(cudaMemcpy(h->dTables, tb.data(), tb.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
-    PB2_CUDA_H(cudaFuncSetAttribute(pb2::dmma_kernel(h->plan.NT, h->plan.W),
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+    if (h->plan.persistent_ok)
+      PB2_CUDA_H(cudaFuncSetAttribute(pb2::dmma_kernel(h->plan.NT, h->plan.W),
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
     PB2_CUDA_H(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, d.device));
     if (const char* env = std::getenv("PB2_GPC")) h->gpc_override = std::atoi(env);
     if (const char* env = std::getenv("PB2_STAGGER")) h->stagger = std::atoi(env);

@@ -27,15 +27,15 @@ def make(p, algorithm="auto", **kw):
 
 
 def algorithms(p):
-    """Every kind is checked through both the jet kernels and whatever `auto` ships (for b <= 16 with sparse
+    """Every kind is checked through both the jet kernels and whatever `auto` ships (for b <= 24 with sparse
     drive generators -- C4's compact Lindbladian included -- that is the tensor-core kernel)."""
     return ["generic", "auto"]
 
 
 def expected_auto(p):
     """What PB2_ALG_AUTO must select (decided at construction, pb2_api.cu): the tensor-core path for
-    b <= 16 with at most 4 nonzeros per drive-generator row and at most 8 column tiles."""
-    if p.b > 16 or p.n_b > 8:
+    b <= 24 with at most 4 nonzeros per drive-generator row and at most 8 column tiles."""
+    if p.b > 24 or p.n_b > 12:
         return "generic"
     w = max([int((np.asarray(g) != 0).sum(1).max()) for g in p.Gj] + [0])
     ncT = p.b // 2 if p.kind != "density" else p.b
@@ -344,10 +344,10 @@ def test_error_behaviour():
     p, Z, mu = C.trajectory(1, 5)
     with pytest.raises(pb.PB2Error):
         pb.B200BilinearIntegrator("unitary", p.G0, list(p.Gj), K=5, D=3, x_off=0, dt_off=8, u_off=10)
-    big = np.zeros((18, 18))   # the tensor-core path refuses what it cannot do (b > 16)
+    big = np.zeros((26, 26))   # the tensor-core path refuses what it cannot do (b > 24)
     with pytest.raises(pb.PB2Error):
-        pb.B200BilinearIntegrator("density", big, [big], K=5, D=18 + 5, x_off=0, dt_off=18,
-                                  u_off=20, algorithm="dmma")
+        pb.B200BilinearIntegrator("density", big, [big], K=5, D=26 + 5, x_off=0, dt_off=26,
+                                  u_off=28, algorithm="dmma")
     B = make(p)
     with pytest.raises(ValueError):
         B.residual_jacobian(Z[:, :3])
@@ -391,13 +391,15 @@ def _random_problem(kind, b, m, K, seed):
 
 @pytest.mark.parametrize("kind,b,m", [("density", 9, 2), ("density", 4, 1), ("density", 16, 3),
                                       ("density", 5, 0), ("ket", 6, 2), ("ket", 16, 3), ("ket", 2, 1),
-                                      ("unitary", 6, 2), ("unitary", 12, 1), ("unitary", 16, 6)])
+                                      ("unitary", 6, 2), ("unitary", 12, 1), ("unitary", 16, 6),
+                                      ("ket", 18, 4), ("unitary", 18, 2), ("density", 24, 1), ("ket", 22, 0),
+                                      ("unitary", 20, 1)])
 def test_tensor_core_path_shapes(kind, b, m, monkeypatch):
     """Odd / padded generator sizes, m = 0, mixed tiles (propagator, state and jet columns sharing
     one 8-column tile), the widest supported problem (8 tiles) -- through the default small-CTA kernel (knot_dmmaq)
     and through the persistent pipelined one (knot_dmma, PB2_DMMAQ=0)."""
     p, Z, mu = _random_problem(kind, b, m, 9, seed=100 * b + m)
-    for env in (None, "0"):
+    for env in (None, "0"):      # (17 <= b <= 24, two-transmon qutrit sizes: only the small-CTA kernel exists)
         if env is not None:
             monkeypatch.setenv("PB2_DMMAQ", env)
         B = make(p, "dmma")
@@ -1644,7 +1646,8 @@ def test_host_pointer_pipeline_pinned_and_pageable(monkeypatch):
 
 @pytest.mark.parametrize("kind,b,m", [("density", 9, 2), ("density", 4, 1), ("density", 16, 3), ("density", 5, 0),
                                       ("ket", 6, 2), ("ket", 16, 3), ("ket", 2, 1), ("ket", 8, 6),
-                                      ("unitary", 6, 2), ("unitary", 4, 3), ("unitary", 8, 4), ("unitary", 12, 1)])
+                                      ("unitary", 6, 2), ("unitary", 4, 3), ("unitary", 8, 4), ("unitary", 12, 1),
+                                      ("ket", 18, 4), ("density", 24, 2), ("unitary", 18, 1), ("ket", 20, 0)])
 def test_tensor_core_hessian_shapes(kind, b, m, monkeypatch):
     """Row a8 on the tensor cores for general generators (knot_dmmah.cuh): forward tiles (state, first- and
     second-order jets) and adjoint tiles with the TRANSPOSED generator -- no symmetry assumed (density generators
