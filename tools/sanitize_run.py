@@ -39,4 +39,45 @@ for cfg, K in ((3, 700), (2, 60), (4, 50), (1, 20)):
              + pb.LeakageObjective([0, 1], "x", traj, times=[0, K // 2, K - 1]))
         J.value_gradient(Z)
         J.value(Z)
+        J.hessian_values(Z, 0.7)
         J.close()
+    # round 2: equal-timestep rows, rollout, dense d/dx_k block, an ensemble in one launch, time-dependent drives,
+    # the older kernels behind their switches
+    L = pb.B200KnotLinearConstraints(traj, timesteps_all_equal=True)
+    L.residual_jacobian(Z)
+    L.close()
+    B = pb.B200BilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off, dt_off=p.dt_off, u_off=p.u_off,
+                                  dense_blocks=True)
+    B.residual_jacobian(Z)
+    B.rollout(Z)
+    B.close()
+    if cfg in (1, 2, 4):
+        import dataclasses
+        n, n_x = 3, p.n_x
+        Zs = np.zeros((n * n_x + p.D - n_x, p.K), order="F")
+        Zs[n * n_x:] = Z[n_x:]
+        for i in range(n):
+            Zs[i * n_x:(i + 1) * n_x] = Z[:n_x]
+        batch = pb.B200IntegratorBatch(p.kind, [(p.G0 * (1 + 0.1 * i), list(p.Gj)) for i in range(n)], K=p.K, D=Zs.shape[0],
+                                       x_offs=[i * n_x for i in range(n)], dt_off=p.dt_off + (n - 1) * n_x,
+                                       u_off=p.u_off + (n - 1) * n_x)
+        batch.residual_jacobian(Zs)
+        batch.hessian_values(Zs, np.ones((n, batch.dim)))
+        batch.close()
+    if p.kind != "density":
+        mods = [(lambda t, w=0.3 * (j + 1): np.cos(w * t)) for j in range(p.m)]
+        Bt = pb.B200BilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off, dt_off=p.dt_off,
+                                       u_off=p.u_off, t_off=p.dt_off + 1, modulations=mods)
+        Bt.residual_jacobian(Z)
+        Bt.close()
+for env in ({"PB2_DMMAQ": "0"}, {"PB2_U8Q_NS": "2"}, {"PB2_U8Q": "0"}, {"PB2_NO_DMMAH": "1"}, {"PB2_HESS_DMMAH": "1"}):
+    os.environ.update(env)
+    for cfg, K in ((3, 150), (2, 40), (4, 30)):
+        p, Z, mu = C.trajectory(cfg, K)
+        B = pb.B200BilinearIntegrator(p.kind, p.G0, list(p.Gj), K=p.K, D=p.D, x_off=p.x_off, dt_off=p.dt_off, u_off=p.u_off)
+        B.residual_jacobian(Z)
+        B.hessian_values(Z, mu)
+        print(env, cfg, B.algorithm, B.hessian_algorithm)
+        B.close()
+    for k in env:
+        del os.environ[k]
