@@ -4,7 +4,7 @@
 // truncated-Taylor action of exp(dt G(u)) on the stacked columns [I | X | jet_1 .. jet_m] by DMMA.8x8x4 on
 // register-resident transposed tiles; it replaces DirectTrajOpt's BilinearIntegrator evaluation as built at
 // /root/reference/src/control/integrators.jl:35-51 -- organised around what the traces of knot_u8 and of the
-// first single-round draft showed (tools/trace_u8s.py):
+// first single-round draft showed (tools/trace_u8p.py):
 //
 //   * with 6.75 knots per SM a persistent kernel that keeps four knots in flight runs two rounds, the second
 //     one latency-bound; here EVERY knot of the SM is in flight at once, one slot per knot;

@@ -4,7 +4,7 @@
 // Same mathematics as knot_u8.cuh / knot_u8p.cuh (truncated-Taylor action of exp(dt G(u)) on the stacked columns
 // [I | X | jet_1 .. jet_m] by DMMA.8x8x4 on register-resident transposed tiles; it replaces DirectTrajOpt's
 // BilinearIntegrator evaluation as built at /root/reference/src/control/integrators.jl:35-51).  What the traces of
-// the one-CTA-per-SM kernels showed (tools/trace_u8s.py): with every knot of an SM in flight
+// the one-CTA-per-SM kernels showed (tools/trace_u8p.py): with every knot of an SM in flight
 // the Horner phase runs at ~86 % of the FP64 tensor pipe, but a quarter of a launch is spent where the pipe idles --
 // the launch gap between two grids on an SM (~750 cycles), the HBM latency of the knot slabs (~1 800), the
 // generator build (~1 300) and the tail -- and a 512-thread CTA that owns the whole register file cannot overlap

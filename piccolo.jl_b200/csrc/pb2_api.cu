@@ -31,7 +31,6 @@
 #include "knot_objective.cuh"
 #include "knot_rollout.cuh"
 #include "knot_td.cuh"
-#include "knot_u8s.cuh"
 #include "knot_u8p.cuh"
 #include "knot_u8q.cuh"
 #include "host_pool.h"
@@ -188,7 +187,6 @@ struct pb2_handle {
   int pdl = 1;
   int stagger_g = 0;
   int direct_last = 1;
-  int u8s = 0;             // first single-round draft (whole-knot slots), kept for A/B measurements (PB2_U8S=1)
   int u8p = 1;             // single-round kernel for <= 7 knots per SM (knot_u8p.cuh); PB2_U8P=0 disables it
   int u8q = 2;             // small-CTA kernel (knot_u8q.cuh): 2 = every size, 1 = at most 7 knots per SM, 0 = off (PB2_U8Q)
   int u8q_ns = 1;          // knots per CTA: 1 (eight 64-thread CTAs per SM, the default), 2 or 4; PB2_U8Q_NS
@@ -303,7 +301,7 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
   // (when even four knots per CTA do not fit, the column is too long for any of the slab-staging 3-qubit kernels: the
   // general kernel, which reads the trajectory straight from global memory, takes the call)
   const bool slab_fits = !(h->u8p_ok && h->u8q) || u8q_ns != 0;
-  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8q && u8q_ns && !h->u8s && djac && aligned16 && (p.D % 2 == 0) &&
+  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8q && u8q_ns && djac && aligned16 && (p.D % 2 == 0) &&
       (p.x_off % 2 == 0) && (n_peers == 0 || !std::getenv("PB2_U8Q_NO_PEERS")) &&
       (h->u8q >= 2 || h->nk() <= (int64_t)7 * h->n_sm)) {
     // two 256-thread CTAs per SM, at most four knots each: one CTA's prologue and tail run underneath the
@@ -359,7 +357,7 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
     h->launches++;
     return PB2_OK;
   }
-  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8p && !h->u8s && djac && aligned16 && slab_fits && (p.D % 2 == 0) &&
+  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8p_ok && h->u8p && djac && aligned16 && slab_fits && (p.D % 2 == 0) &&
       (p.x_off % 2 == 0) && n_peers == 0 && h->nk() <= (int64_t)pb2::kU8pSlots * h->n_sm) {
     // at most seven knots per SM: every knot of an SM in flight at once, propagator tiles first (knot_u8p.cuh)
     pb2::U8pParams q{};
@@ -392,37 +390,7 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
     h->launches++;
     return PB2_OK;
   }
-  if (h->alg == PB2_ALG_DMMA && h->u8_ok && h->u8s && djac && aligned16 && slab_fits && (p.D % 2 == 0) && (p.x_off % 2 == 0) &&
-      (p.m == 3 || p.m == 4) && !compact && n_peers == 0 &&
-      h->nk() <= (int64_t)pb2::kU8sSlots * h->n_sm) {
-    // at most seven knots per SM: single-round kernel, every knot of an SM in flight (EXPERIMENTAL, PB2_U8S=1)
-    pb2::U8sParams q{};
-    q.m = p.m; q.D = p.D; q.x_off = p.x_off; q.dt_off = p.dt_off; q.u_off = p.u_off;
-    q.nnz_jac = p.nnz_jac; q.max_sub = 4096; q.nk = (int)h->nk();
-    q.zlen = p.D + p.x_off + 128;
-    q.tables = h->dTables; q.ell = h->dEll;
-    q.Z = dZ; q.delta = ddelta; q.jac = djac;
-#ifdef PB2_TRACE
-    q.trace = h->dTrace3; q.trace_id = (h->trace_launch++) % 64;
-#endif
-    const size_t smem = pb2::u8s_layout(q);
-    if (smem > kSmemLimit) return fail(PB2_EINVAL, "u8s resjac: knot column too large for the shared-memory staging");
-    auto kern = pb2::u8s_kernel(h->plan.W);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)std::min<int64_t>(h->n_sm, q.nk));
-    cfg.blockDim = dim3(64 * pb2::kU8sSlots);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = h->pdl ? 1 : 0;
-    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, kern, q);
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(PB2_ECUDA, std::string("u8s resjac launch: ") + cudaGetErrorString(e));
-  } else if (h->alg == PB2_ALG_DMMA && h->u8_ok && djac && aligned16 && slab_fits && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
+  if (h->alg == PB2_ALG_DMMA && h->u8_ok && djac && aligned16 && slab_fits && (p.D % 2 == 0) && (p.x_off % 2 == 0)) {
     // the 3-qubit unitary shape: warp-specialised kernel (producer warp + (E,X) warp + jet warps)
     const pb2::DmmaPlan& pl = h->plan;
     pb2::U8Params q{};
@@ -846,7 +814,6 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
     if (const char* env = std::getenv("PB2_PDL")) h->pdl = std::atoi(env);
     if (const char* env = std::getenv("PB2_STAGGER_G")) h->stagger_g = std::atoi(env);
     if (const char* env = std::getenv("PB2_DIRECT_LAST")) h->direct_last = std::atoi(env);
-    if (const char* env = std::getenv("PB2_U8S")) h->u8s = std::atoi(env);
     if (const char* env = std::getenv("PB2_U8P")) h->u8p = std::atoi(env);
     if (const char* env = std::getenv("PB2_U8Q")) h->u8q = std::atoi(env);
     if (const char* env = std::getenv("PB2_U8Q_NS")) {

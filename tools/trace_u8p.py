@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Debug: clock64 stamps of every CTA of the single-round residual+Jacobian kernel over a CUDA graph of
+"""Debug: clock64 stamps of every CTA of the one-CTA-per-SM single-round kernel (knot_u8p; run with PB2_U8Q=0) over a CUDA graph of
 back-to-back launches (the benchmarked configuration), keyed by %smid so that the gap between one launch's
 CTA exit and the next launch's CTA entry ON THE SAME SM can be read off (clock64 is a per-SM free-running
 counter).  Needs the debug build: make -C piccolo.jl_b200 libpiccolo_b200_trace.so"""
@@ -42,15 +42,9 @@ torch.cuda.synchronize()
 assert lib.pb2_debug_trace3(B._h, out.ctypes.data) == 0
 T = out[:64 * 148 * 16 * 8].reshape(64, 148, 16, 8)[:NL]
 S = out[64 * 148 * 16 * 8:].reshape(64, 148, 16, 32)[:NL]
-U8P = os.environ.get("PB2_U8S", "0") != "1"      # default: the shipped single-round kernel (knot_u8p)
-if U8P:
-    names = ["entry", "armed", "landed", "prepared", "E_done", "horner_end", "slab_issue", "end"]
-    smid = T[:, :, 12, 6]
-    END = 7
-else:
-    names = ["entry", "armed", "landed", "prepared", "horner_end", "end", "after_wait"]
-    smid = T[:, :, 0, 7]
-    END = 5
+names = ["entry", "armed", "landed", "prepared", "E_done", "horner_end", "slab_issue", "end"]
+smid = T[:, :, 12, 6]
+END = 7
 print("launch, block -> smid constant across launches:", bool((smid == smid[0]).all()))
 # per launch, per block: entry (min over warps), end (max over warps)
 ent = np.where(T[..., 0] > 0, T[..., 0], np.iinfo(np.int64).max).min(axis=2)
@@ -80,7 +74,7 @@ for b in (0, 1, 50, 110, 111, 147):
     print(f"launch {l} block {b} smid {int(smid[l, b])} duration {int(dur[l, b])}")
     print("\n".join(rows))
 
-if U8P:
+if True:
     print("per-step stamps (start of step, after the exchange barrier), cycles since CTA entry; launch", l)
     for b in (0, 50):
         for w in range(16):
