@@ -391,3 +391,17 @@ def test_objective_hessians_against_central_differences():
             dm[t] -= h
             gp, gm = OB.quadratic_regularizer(V, dp, R, base, pw), OB.quadratic_regularizer(V, dm, R, base, pw)
             assert abs((gp[2][t] - gm[2][t]) / (2 * h) - dtt[t]) < 1e-7
+
+
+def test_hessian_adjoint_pairing_matches_frechet_oracle():
+    """oracle/hessian_pairing.py (adjoint Horner iterates paired with forward power jets: no second-order jets) against
+    the Pade / Frechet statement, on a unitary, a ket and a non-normal density generator."""
+    from oracle import hessian_pairing as HP
+    import dataclasses
+    for cfg, K in ((1, 6), (2, 5), (4, 5), (6, 5)):
+        p, Z, mu = C.trajectory(cfg)              # BASELINE time steps (a short K would stretch dt: ||dt G|| ~ 56 for C4)
+        p = dataclasses.replace(p, K=K)
+        Z, mu = np.asfortranarray(Z[:, :K]), mu[:p.dim]
+        h = HP.hessian_values(p, Z, mu)
+        ho = KN.hessian_values(p, Z, mu)
+        assert np.abs(h - ho).max() < 1e-9 * max(1.0, np.abs(ho).max())
