@@ -537,16 +537,26 @@ def run_ours(args):
             del gi
             # the five callbacks of an iterate are independent of one another (same trajectory in, disjoint outputs):
             # as parallel branches of the graph the iterate costs about its longest member, the Hessian
-            sides = [torch.cuda.Stream(device=dev) for _ in range(4)]
+            # (the 3-qubit Hessian kernel needs a whole SM per CTA: it runs on a high-priority branch and leaves
+            # PB2_BENCH_HESS_RESERVE SMs to the other four callbacks, PB2_OPT_HESSIAN_CTAS)
+            n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+            # one knot more per Hessian CTA than the full machine would give: C3, 999 knots -> 8 instead of 7 per CTA
+            # -> 125 CTAs, 23 SMs left to the other callbacks
+            kp = -(-n_eval // n_sm) + 1
+            reserve = int(os.environ.get("PB2_BENCH_HESS_RESERVE", str(max(0, n_sm - (-(-n_eval // kp))))))
+            if B.hessian_algorithm == "u8h" and 0 < reserve < n_sm:
+                B.set_option("hessian_ctas", n_sm - reserve)
+            sides = [torch.cuda.Stream(device=dev) for _ in range(2)] + [torch.cuda.Stream(device=dev, priority=-1)] + \
+                    [torch.cuda.Stream(device=dev)]
 
             def one_iterate_par(i, main):
                 s_ = i % nsets
                 for sd in sides:
                     sd.wait_stream(main)
+                B.hessian_device(Zs[s_], dmu, dH[i & 1], sides[2].cuda_stream)
                 B.residual_jacobian_device(Zs[s_], outs[s_][:B.dim], outs[s_][B.dim:], main.cuda_stream)
                 Lc.residual_jacobian_device(Zs[s_], dLd, dLv, sides[0].cuda_stream)
                 Jobj.value_gradient_device(Zs[s_], dJ, dG[i & 1], sides[1].cuda_stream)
-                B.hessian_device(Zs[s_], dmu, dH[i & 1], sides[2].cuda_stream)
                 Jobj.hessian_device(Zs[s_], 1.0, dOh, sides[3].cuda_stream)
                 for sd in sides:
                     main.wait_stream(sd)
@@ -563,11 +573,13 @@ def run_ours(args):
             torch.cuda.synchronize()
             itp_ms = ev[0].elapsed_time(ev[1]) / isteps
             del gp
+            B.set_option("hessian_ctas", 0)
             iterate = {"ms_per_iterate": it_ms, "ms_per_iterate_concurrent": itp_ms, "launches_per_iterate": 5,
                        "calls": "residual+Jacobian (dynamics), residual+Jacobian (derivative pairs, time consistency), "
                                 "objective value+gradient, Lagrangian Hessian (dynamics), objective Hessian; "
                                 "one resident trajectory; ms_per_iterate: one stream, ms_per_iterate_concurrent: the five "
-                                "as parallel branches of the graph"}
+                                "as parallel branches of the graph (the 3-qubit Hessian kernel on a high-priority branch "
+                                "and on all but %d SMs)" % reserve}
             Lc.close()
         objective["nlp_iterate"] = iterate
         Jobj.close()

@@ -200,8 +200,12 @@ int pb2_sync(pb2_handle* h);
  *                     at all, so consecutive calls overlap freely (one grid's tail under the next one's products) and
  *                     need not complete in order.  Later stream operations are ordered after both as usual.
  * The host-pointer entry points always run in the second mode: the library itself copies Z to, and the results from,
- * its own buffers on the handle's stream. */
-enum { PB2_OPT_EARLY_Z = 1, PB2_OPT_PIPELINED = 2 };
+ * its own buffers on the handle's stream.
+ *  PB2_OPT_HESSIAN_CTAS  value = how many SMs the persistent 3-qubit Hessian kernel may occupy (0: all).  That kernel
+ *                     needs a whole SM per CTA, so nothing else runs beside it; a caller that enqueues the other
+ *                     callbacks of the same NLP iterate on other streams (they are independent) leaves them some SMs
+ *                     this way: C3, 116 of 148 SMs for the Hessian -> the iterate costs about the Hessian alone. */
+enum { PB2_OPT_EARLY_Z = 1, PB2_OPT_PIPELINED = 2, PB2_OPT_HESSIAN_CTAS = 3 };
 int pb2_set_option(pb2_handle* h, int32_t option, int64_t value);
 
 /* Time-dependent handles: the modulation values at the trajectory's CURRENT time row, c[j + m k] = c_j(t_k) and

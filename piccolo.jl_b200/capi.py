@@ -11,7 +11,7 @@ PB2_HOST, PB2_DEVICE = 0, 1
 PB2_ALG_AUTO, PB2_ALG_GENERIC, PB2_ALG_DMMA = 0, 1, 2
 KIND = {"ket": PB2_KET, "unitary": PB2_UNITARY, "density": PB2_DENSITY}
 ALG = {"auto": PB2_ALG_AUTO, "generic": PB2_ALG_GENERIC, "dmma": PB2_ALG_DMMA}
-OPT = {"early_z": 1, "pipelined": 2}
+OPT = {"early_z": 1, "pipelined": 2, "hessian_ctas": 3}
 
 # every symbol include/piccolo_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [

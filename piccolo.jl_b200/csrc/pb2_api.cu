@@ -199,6 +199,7 @@ struct pb2_handle {
   double u8p_cj[4] = {1.0, 1.0, 1.0, 1.0};
   long long xchg_flag_off = -1;   // set around an exchange_sync launch
   int early_z = 0;         // PB2_OPT_EARLY_Z: device-pointer calls may read Z before the programmatic dependency wait
+  int hess_ctas = 0;       // PB2_OPT_HESSIAN_CTAS: SMs the persistent Hessian kernel may take (0: all)
   int pipelined = 0;       // PB2_OPT_PIPELINED: no dependency wait at all (outputs not shared with the preceding kernel)
   pb2::EllEntry* dEll = nullptr;
   // staging for host-pointer calls
@@ -547,7 +548,7 @@ int launch_hess(pb2_handle* h, const double* dZ, const double* dmu, double* dhes
     q.Z = dZ; q.mu = dmu; q.hess = dhess; q.trace = h->dTrace2;
     const size_t smem = pb2::u8h_layout(q);
     if (smem > kSmemLimit) return fail(PB2_EINVAL, "u8h hessian: knot column too large for the shared-memory staging");
-    const int blocks = std::min(h->n_sm, q.nk);
+    const int blocks = std::min(h->hess_ctas > 0 ? std::min(h->hess_ctas, h->n_sm) : h->n_sm, q.nk);
     pb2::u8h_kernel(h->plan.W)<<<blocks, 32 * (1 + q.ncw), smem, st>>>(q);
     PB2_CUDA(cudaGetLastError());
     h->launches++;
@@ -1132,6 +1133,10 @@ int pb2_set_option(pb2_handle* h, int32_t option, int64_t value) {
   switch (option) {
     case PB2_OPT_EARLY_Z: h->early_z = value != 0; return PB2_OK;
     case PB2_OPT_PIPELINED: h->pipelined = value != 0; return PB2_OK;
+    case PB2_OPT_HESSIAN_CTAS:
+      if (value < 0) return fail(PB2_EINVAL, "pb2_set_option: PB2_OPT_HESSIAN_CTAS needs a count >= 0");
+      h->hess_ctas = (int)std::min<int64_t>(value, 1 << 20);
+      return PB2_OK;
     default: return fail(PB2_EINVAL, "pb2_set_option: unknown option");
   }
 }
