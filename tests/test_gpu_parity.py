@@ -1744,3 +1744,19 @@ def test_single_knot_ctas_and_long_knot_columns():
             ho = KN.hessian_values(p, Z, mu)
             assert np.abs(B.hessian_values(Z, mu) - ho).max() < HESS_RTOL * max(1.0, np.abs(ho).max())
         B.close()
+
+
+def test_hessian_cta_cap_option():
+    """PB2_OPT_HESSIAN_CTAS only changes how many SMs the persistent 3-qubit Hessian kernel occupies, never the values;
+    a negative count is refused."""
+    p, Z, mu = C.trajectory(3, 400)
+    B = make(p)
+    h0 = B.hessian_values(Z, mu)
+    for n in (1, 37, 125, 10000):
+        B.set_option("hessian_ctas", n)
+        assert np.array_equal(B.hessian_values(Z, mu), h0)
+    B.set_option("hessian_ctas", 0)
+    assert np.array_equal(B.hessian_values(Z, mu), h0)
+    with pytest.raises(pb.PB2Error):
+        B.set_option("hessian_ctas", -1)
+    B.close()
