@@ -39,7 +39,6 @@ struct U8qParams {
   int compact;            // 1: records [E columns 0..7 | jets, d/d dt | delta] of cstride doubles go to `jac`
   int cstride;
   int split;              // > 0: CTAs >= split own one slot less than the others (knot = slot * gridDim + block)
-  int space;              // > 0: compute phases of the CTAs sharing an SM start at least `space` cycles apart
   int n_peers;            // > 1 (sharded run, compact records): every record also goes into the gather buffer of each
                           // other rank, peers[r] + slot_off (+ knot * cstride), over NVLink; peers[self] is the local one
   int self;
@@ -50,8 +49,6 @@ struct U8qParams {
                           // words, so when it completes every other rank's records of this step have landed here as
                           // well (no separate barrier kernel)
   int nowait;             // 1: no programmatic dependency wait at all (the caller's promise: PB2_OPT_PIPELINED)
-  int pro;                // typical prologue length in cycles (entry -> first product) the spacing is applied after
-  unsigned long long* sm_clock;   // [512] per-SM reservation word for `space` (clock64 is one counter per SM)
   // shared-memory layout in doubles (u8q_layout)
   int o_norm, o_tab, o_f32, o_slot, slot_stride, zpad, o_prep, o_y, o_est, o_rec, o_mbar;
   double cj[4];           // UNIT: the common magnitude of drive generator j's nonzeros
@@ -191,25 +188,6 @@ __global__ void __launch_bounds__(64 * NS, 8 / NS) knot_u8q_kernel(const __grid_
     u8p_ell(p.ell, 2, g, q, a_y, ev[0], sg[0], yad[0]);
     u8p_ell(p.ell, m >= 4 ? 3 : m, g, q, a_y, ev[1], sg[1], yad[1]);   // drive m is the all-zero dummy
   }
-  if (p.space > 0 && threadIdx.x == 0) {
-    // CTAs that share an SM start their product phases at least `space` cycles apart: in phase they would all
-    // sit in their prologues together and then split the tensor pipe together; out of phase one CTA's slab
-    // latency, generator build and stores run underneath the others' products.  One word per SM holds the next
-    // free start time (clock64 counts per SM); the round trip hides under the slab's latency.
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    unsigned long long* wd = p.sm_clock + (smid & 511u);
-    const unsigned long long now = (unsigned long long)clock64();
-    unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(wd), mine;
-    for (int it = 0; it < 8; ++it) {
-      // a stale word (an earlier launch, long ago, or a wrapped / foreign value) is treated as "free now"
-      mine = (old > now && old - now < 16ull * (unsigned long long)p.space) ? old : now;
-      const unsigned long long prev = atomicCAS(wd, old, mine + (unsigned long long)p.space);
-      if (prev == old) break;
-      old = prev;
-    }
-    *reinterpret_cast<volatile unsigned long long*>(u8q_smem + p.o_f32 + 15) = mine + (unsigned long long)p.pro;
-  }
   __syncthreads();
   U8Q_STAMP(1);
   if (!have) return;                                       // both warps of an empty slot leave together
@@ -302,10 +280,6 @@ __global__ void __launch_bounds__(64 * NS, 8 / NS) knot_u8q_kernel(const __grid_
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int i4 = 0; i4 < 4; ++i4) ev[a][i4] *= dts;
-  }
-  if (p.space > 0) {
-    const unsigned long long go = *reinterpret_cast<volatile unsigned long long*>(u8q_smem + p.o_f32 + 15);
-    while ((unsigned long long)clock64() < go) { }
   }
   U8Q_STAMP(3);
 

@@ -190,8 +190,6 @@ struct pb2_handle {
   int u8p = 1;             // single-round kernel for <= 7 knots per SM (knot_u8p.cuh); PB2_U8P=0 disables it
   int u8q = 2;             // small-CTA kernel (knot_u8q.cuh): 2 = every size, 1 = at most 7 knots per SM, 0 = off (PB2_U8Q)
   int u8q_ns = 1;          // knots per CTA: 1 (eight 64-thread CTAs per SM, the default), 2 or 4; PB2_U8Q_NS
-  int u8q_space = 0;       // minimum spacing (cycles) of the product phases of CTAs sharing an SM; PB2_U8Q_SPACE
-  unsigned long long* dSmClock = nullptr;
   unsigned long long* dSyncWords = nullptr;   // [0] ticket, [1] exchange epoch (knot_u8q.cuh, in-kernel step barrier)
   double* dTablesP = nullptr;   // knot_u8p's table blob (u8p_tables)
   double* dTablesQ = nullptr;   // knot_u8q's table blob (u8q_tables)
@@ -327,9 +325,7 @@ int launch_resjac_core(pb2_handle* h, const double* dZ, double* ddelta, double* 
     q.trace = h->dTrace3; q.trace_id = (h->trace_launch++) % 64;
 #endif
     const int ns = u8q_ns, cps = 8 / ns;   // knots per CTA, CTAs per SM
-    q.space = h->u8q_space; q.sm_clock = h->dSmClock;
     if (const char* env = std::getenv("PB2_NOWAIT")) q.nowait = std::atoi(env);   // (measurement knob)
-    q.pro = std::getenv("PB2_U8Q_PRO") ? std::atoi(std::getenv("PB2_U8Q_PRO")) : 3000;
     unsigned grid;
     if (q.nk <= 7 * h->n_sm) {
       // cps CTAs per SM; the last n_sm CTAs own one knot less: blocks b, b + n_sm, ... share an SM on an idle
@@ -821,7 +817,6 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
       const int v = std::atoi(env);
       h->u8q_ns = (v == 1 || v == 2) ? v : 4;
     }
-    if (const char* env = std::getenv("PB2_U8Q_SPACE")) h->u8q_space = std::atoi(env);
     if (const char* env = std::getenv("PB2_EARLY_Z")) h->early_z = std::atoi(env);
     if (const char* env = std::getenv("PB2_PIPELINED")) h->pipelined = std::atoi(env);
     h->u8_ok = h->plan.iso && d.b == 16 && d.n_b == 8 && d.m >= 1 && d.m <= 6 && !std::getenv("PB2_NO_U8");
@@ -852,8 +847,6 @@ int pb2_create(const pb2_desc* desc, pb2_handle** out) {
         }
         PB2_CUDA_H(cudaMalloc(&h->dSyncWords, 2 * sizeof(unsigned long long)));
         PB2_CUDA_H(cudaMemset(h->dSyncWords, 0, 2 * sizeof(unsigned long long)));
-        PB2_CUDA_H(cudaMalloc(&h->dSmClock, 512 * sizeof(unsigned long long)));
-        PB2_CUDA_H(cudaMemset(h->dSmClock, 0, 512 * sizeof(unsigned long long)));
         h->u8p_ok = true;
       }
     }
@@ -904,7 +897,6 @@ void pb2_destroy(pb2_handle* h) {
   if (h->dTables) cudaFree(h->dTables);
   if (h->dTablesP) cudaFree(h->dTablesP);
   if (h->dTablesQ) cudaFree(h->dTablesQ);
-  if (h->dSmClock) cudaFree(h->dSmClock);
   if (h->dSyncWords) cudaFree(h->dSyncWords);
   if (h->dCanon) cudaFree(h->dCanon);
   for (double* q : {h->dCoef, h->dCoefDot, h->dZs})
