@@ -132,12 +132,15 @@ def run_reference(args):
 
     # a reference "step" is a bounded sample of `passes` whole passes over the trajectory, sized from a
     # calibration pass so that the K timed steps last >= ~3 s (20 single passes were 0.15 s: +-30 % noise)
-    one_pass()
-    t0 = time.perf_counter()
-    for _ in range(3):
+    # (the pool's threads take a few passes to spin up: calibrate on warm passes, and on the FASTEST of them)
+    for _ in range(5):
         one_pass()
-    t_pass = (time.perf_counter() - t0) / 3
-    passes = int(min(400, max(1, np.ceil(3.0 / max(args.steps, 1) / t_pass))))
+    t_pass = float("inf")
+    for _ in range(10):
+        t0 = time.perf_counter()
+        one_pass()
+        t_pass = min(t_pass, time.perf_counter() - t0)
+    passes = int(min(2000, max(1, np.ceil(3.0 / max(args.steps, 1) / t_pass))))
 
     def step():
         for _ in range(passes):
